@@ -1,0 +1,163 @@
+/*
+ * flmr_maxsim.h — C ABI of the B200-native FLMR / ColBERT late-interaction MaxSim + top-k path.
+ *
+ * This is the drop-in boundary for the ONE hot path this repository accelerates
+ * (SURVEY.md §8b).  The reference has no FFI registry for this path: it binds four pybind11
+ * torch extensions and calls Python scoring functions.  Each entry point below names the
+ * reference interface it replaces (paths relative to the reference checkout, `CB/` =
+ * third_party/ColBERT/colbert/):
+ *
+ *   flmr_corpus_create / _destroy / _info
+ *       replaces the PLAID index residency built by IndexScorer.__init__ / IndexLoader
+ *       (CB/search/index_storage.py:21-66, CB/search/index_loader.py:13-86) and the packed
+ *       `D_packed [sum(doclens), dim]` + `D_lengths` operand pair of colbert_score_packed
+ *       (CB/modeling/colbert.py:289-311).
+ *   flmr_maxsim_scores
+ *       replaces colbert_score / colbert_score_reduce / colbert_score_packed
+ *       (CB/modeling/colbert.py:235-311) and the native segmented_maxsim_cpp
+ *       (CB/modeling/segmented_maxsim.cpp:49-93): all-passage MaxSim scores of each query.
+ *   flmr_maxsim_topk
+ *       replaces IndexScorer.rank (CB/search/index_storage.py:86-98: retrieve -> score_pids ->
+ *       sort) as called per query from Searcher.dense_search (CB/searcher.py:91-132); exhaustive
+ *       instead of PLAID-pruned, batched over queries, top-k fused into the scoring kernel.
+ *   flmr_topk_merge
+ *       the only exchange step of the sharded path: merges per-shard top-k lists
+ *       (gathered by the host with one NCCL all-gather) into the global top-k.
+ *   flmr_debug_maxsim_scores_simt
+ *       test infrastructure: an independent plain-SIMT fp32 device kernel used by tests to
+ *       cross-check the tensor-core kernel at sizes where the CPU oracle is too slow.
+ *
+ * Conventions (cf. SURVEY.md §8b "ownership / errors / threading"):
+ *   - plain pointers and sizes only; no torch / C++ types cross this boundary;
+ *   - every function returns an int status (0 = FLMR_OK); no exceptions, aborts or asserts
+ *     cross the boundary; flmr_last_error() returns a thread-local message for the last failure;
+ *   - the caller owns every input and output buffer; "d_" parameters are DEVICE pointers on the
+ *     corpus' device, "h_" parameters are HOST pointers;
+ *   - compute entry points are asynchronous on the supplied CUDA stream (passed as void* so the
+ *     header needs no CUDA include; NULL = default stream);
+ *   - a corpus handle is immutable after creation and may be shared by threads; concurrent
+ *     searches on one handle must use distinct flmr_workspace handles.
+ */
+#ifndef FLMR_MAXSIM_H_
+#define FLMR_MAXSIM_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FLMR_ABI_VERSION 1
+
+/* status codes */
+#define FLMR_OK 0
+#define FLMR_ERR_INVALID_ARG 1
+#define FLMR_ERR_CUDA 2
+#define FLMR_ERR_UNSUPPORTED 3
+#define FLMR_ERR_OOM 4
+#define FLMR_ERR_KERNEL 5 /* device-side watchdog / self-check tripped */
+
+/* flags for flmr_maxsim_scores / flmr_maxsim_topk */
+#define FLMR_FLAG_RELU 1u /* reproduce the reference CPU packed path: sum_i max(0, max_j s_ij)   \
+                             (CB/modeling/segmented_maxsim.cpp:58-59 zero-initialises the max) */
+
+/* flags for flmr_corpus_create */
+#define FLMR_CORPUS_COPY 0u  /* always copy the token matrix into library-owned HBM            */
+#define FLMR_CORPUS_ADOPT 1u /* tokens is a device pointer; keep it (zero-copy) when every     \
+                                doclen is a multiple of FLMR_TOKEN_GROUP, else copy+repack     */
+
+#define FLMR_DIM 128        /* embedding dim of FLMR / ColBERT (CB/infra/config/settings.py:101) */
+#define FLMR_TOKEN_GROUP 4  /* passages are stored padded to a multiple of this many tokens     */
+#define FLMR_MAX_K 128      /* largest k of the fused top-k                                     */
+
+typedef struct flmr_corpus flmr_corpus_t;       /* resident passage-token shard            */
+typedef struct flmr_workspace flmr_workspace_t; /* per-caller scratch (candidates, Q pad)  */
+
+typedef struct flmr_corpus_info {
+  int64_t n_passages;     /* passages in this shard                                           */
+  int64_t n_tokens;       /* real tokens (sum of doclens)                                     */
+  int64_t n_rows;         /* stored rows (tokens incl. group padding)                         */
+  int64_t pid_base;       /* global id of passage 0 of this shard                             */
+  int32_t dim;            /* = FLMR_DIM                                                       */
+  int32_t device;         /* CUDA device ordinal                                              */
+  int32_t n_ctas;         /* persistent CTAs the scan kernel launches (= SMs of the device)   */
+  int32_t adopted;        /* 1 if the token matrix is the caller's buffer (zero-copy)         */
+  int64_t n_tiles;        /* passage-token tiles streamed per corpus pass                     */
+  int64_t hbm_bytes;      /* bytes of HBM held by the handle (excluding an adopted matrix)    */
+} flmr_corpus_info_t;
+
+/* Thread-local description of the last error returned on this thread ("" if none). */
+const char* flmr_last_error(void);
+
+/* ABI version of the loaded library (== FLMR_ABI_VERSION it was built with). */
+int flmr_abi_version(void);
+
+/*
+ * Create a resident corpus shard from a packed token matrix.
+ *   tokens      bf16 [sum(h_doclens), dim] row-major, passage after passage.  Host or device
+ *               pointer (detected); with FLMR_CORPUS_ADOPT it must be a device pointer on `device`
+ *               that outlives the handle.
+ *   h_doclens   int32 [n_passages], every entry >= 1 (a zero-length passage has no defined score
+ *               on the reference's two paths, SURVEY.md §8a, and is rejected).
+ *   pid_base    added to local passage indices in every returned id (shard offset, §8e).
+ */
+int flmr_corpus_create(const void* tokens, const int32_t* h_doclens, int64_t n_passages, int dim,
+                       int device, int64_t pid_base, unsigned flags, flmr_corpus_t** out);
+int flmr_corpus_destroy(flmr_corpus_t* corpus);
+int flmr_corpus_info(const flmr_corpus_t* corpus, flmr_corpus_info_t* out);
+
+/* Scratch for searches on `corpus` with up to max_queries x max_nq query tokens per call. */
+int flmr_workspace_create(const flmr_corpus_t* corpus, int max_queries, int max_nq,
+                          flmr_workspace_t** out);
+int flmr_workspace_destroy(flmr_workspace_t* ws);
+/* Device-side watchdog code of the last scan on this workspace (0 = none; 101 producer, 102 MMA
+ * issuer, 103 epilogue starved).  Readable even after the launch trapped. */
+int flmr_workspace_status(const flmr_workspace_t* ws, int* out);
+
+/*
+ * MaxSim scores of every passage for each of n_queries queries.
+ *   d_q          bf16 [n_queries, nq, dim] (rows L2-normalised by the encoder; all-zero rows allowed
+ *                and contribute exactly 0, as in the reference)
+ *   d_out_scores fp32 [n_queries, n_passages]:  out[b][p] = sum_i max_{j<len_p} <Q_b,i , D_p,j>
+ */
+int flmr_maxsim_scores(const flmr_corpus_t* corpus, flmr_workspace_t* ws, const void* d_q,
+                       int n_queries, int nq, unsigned flags, float* d_out_scores, void* stream);
+
+/*
+ * Fused MaxSim + top-k: the k best passages of each query, sorted by descending score
+ * (ties: ascending id).  No score matrix is written to HBM when nq fits one resident query tile.
+ *   d_out_scores fp32  [n_queries, k]
+ *   d_out_pids   int64 [n_queries, k]  (pid_base + local index; -1 / -inf fill if n_passages < k)
+ */
+int flmr_maxsim_topk(const flmr_corpus_t* corpus, flmr_workspace_t* ws, const void* d_q,
+                     int n_queries, int nq, int k, unsigned flags, float* d_out_scores,
+                     int64_t* d_out_pids, void* stream);
+
+/*
+ * Merge n_lists candidate lists per query into one top-k (the post-all-gather step of the
+ * sharded path).  Entries with pid < 0 are ignored.
+ *   d_in_scores fp32  [n_lists, n_queries, k_in]     d_in_pids int64 [n_lists, n_queries, k_in]
+ *   d_out_*           [n_queries, k_out], k_out <= FLMR_MAX_K, n_lists * k_in <= 20480
+ */
+int flmr_topk_merge(const float* d_in_scores, const int64_t* d_in_pids, int n_lists, int n_queries,
+                    int k_in, int k_out, float* d_out_scores, int64_t* d_out_pids, int device,
+                    void* stream);
+
+/* Test infrastructure: plain SIMT fp32 MaxSim of every passage (same contract as
+ * flmr_maxsim_scores), independent of the tensor-core kernel. */
+int flmr_debug_maxsim_scores_simt(const flmr_corpus_t* corpus, const void* d_q, int n_queries,
+                                  int nq, unsigned flags, float* d_out_scores, void* stream);
+
+/* Kernels launched by this library on the calling thread since the last reset (bench evidence). */
+int64_t flmr_launch_count(int reset);
+
+/* Average device time (ms) of the scan kernel launches recorded since the last reset, measured
+ * with CUDA events on the launching stream; requires flmr_set_profiling(1). */
+int flmr_set_profiling(int enable);
+int flmr_scan_kernel_stats(double* total_ms, int64_t* launches, int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FLMR_MAXSIM_H_ */

@@ -1,0 +1,7 @@
+"""B200-native FLMR / ColBERT late-interaction MaxSim + top-k (the one hot path of RA-VQA this
+repository accelerates).  Import name: ``ravqa_b200`` (the directory name carries hyphens)."""
+from . import _cabi  # noqa: F401
+from .corpus import FlatCorpus  # noqa: F401
+from .maxsim import maxsim_scores, maxsim_topk, topk_merge, debug_scores_simt  # noqa: F401
+
+__all__ = ["FlatCorpus", "maxsim_scores", "maxsim_topk", "topk_merge", "debug_scores_simt"]

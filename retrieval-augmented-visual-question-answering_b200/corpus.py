@@ -1,0 +1,121 @@
+"""Resident passage-token corpus shard (replaces the PLAID index residency of the reference:
+``IndexScorer.__init__`` / ``IndexLoader``, third_party/ColBERT/colbert/search/index_storage.py:21-66,
+index_loader.py:13-86).
+
+The reference keeps centroids + residual codes + an IVF and decompresses ~256 survivors per query;
+here the whole shard is a flat bf16 ``[sum(doclens), 128]`` matrix in HBM plus ``doclens`` — exactly
+the ``(D_packed, D_lengths)`` operand pair of ``colbert_score_packed`` (colbert/modeling/colbert.py:289)
+— scanned exhaustively by the fused kernel.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence, Union
+
+import numpy as np
+import torch
+
+from . import _cabi
+
+
+def _as_doclens(doclens) -> np.ndarray:
+    if isinstance(doclens, torch.Tensor):
+        doclens = doclens.detach().cpu().numpy()
+    arr = np.ascontiguousarray(np.asarray(doclens), dtype=np.int32)
+    if arr.ndim != 1:
+        raise ValueError("doclens must be 1-D")
+    return arr
+
+
+class FlatCorpus:
+    """One GPU's shard of the passage-token matrix, resident in HBM.
+
+    tokens   : ``[sum(doclens), 128]`` tensor (bf16 preferred; fp16/fp32 are rounded to bf16), on CPU
+               or on the target GPU.  A CUDA bf16 tensor whose doclens are all multiples of 4 is
+               adopted zero-copy (and kept alive by this object).
+    doclens  : per-passage token counts (>= 1 each).
+    pid_base : global id of this shard's first passage (sharded search).
+    """
+
+    def __init__(self, tokens: torch.Tensor, doclens, device: Optional[Union[int, torch.device]] = None,
+                 pid_base: int = 0, adopt: bool = True):
+        if not torch.cuda.is_available():
+            raise RuntimeError("FlatCorpus needs a CUDA device: there is no CPU fallback for this path")
+        L = _cabi.lib()
+        self.doclens = _as_doclens(doclens)
+        if tokens.dim() != 2 or tokens.size(1) != _cabi.DIM:
+            raise ValueError("tokens must be [sum(doclens), %d], got %s" % (_cabi.DIM, tuple(tokens.shape)))
+        if int(self.doclens.sum()) != tokens.size(0):
+            raise ValueError("sum(doclens)=%d != tokens rows=%d" % (int(self.doclens.sum()), tokens.size(0)))
+        if device is None:
+            device = tokens.device if tokens.is_cuda else torch.device("cuda", torch.cuda.current_device())
+        device = torch.device(device) if not isinstance(device, torch.device) else device
+        if device.index is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        self.device = device
+        tokens = tokens.detach()
+        if tokens.dtype != torch.bfloat16:
+            tokens = tokens.to(torch.bfloat16)
+        tokens = tokens.contiguous()
+        if tokens.is_cuda and tokens.device != device:
+            tokens = tokens.to(device)
+        flags = _cabi.CORPUS_ADOPT if (adopt and tokens.is_cuda) else _cabi.CORPUS_COPY
+        if tokens.is_cuda:
+            torch.cuda.current_stream(device).synchronize()  # producer kernels of `tokens` are done
+        handle = C.c_void_p()
+        _cabi.check(L.flmr_corpus_create(C.c_void_p(tokens.data_ptr()),
+                                         self.doclens.ctypes.data_as(C.c_void_p),
+                                         int(self.doclens.shape[0]), _cabi.DIM, int(device.index),
+                                         int(pid_base), flags, C.byref(handle)))
+        self._h = handle
+        info = _cabi.CorpusInfo()
+        _cabi.check(L.flmr_corpus_info(self._h, C.byref(info)))
+        self.info = info
+        self._keepalive = tokens if info.adopted else None
+        self._ws = None
+        self.pid_base = int(pid_base)
+
+    # -- properties ---------------------------------------------------------------------------
+    @property
+    def n_passages(self) -> int:
+        return int(self.info.n_passages)
+
+    @property
+    def n_tokens(self) -> int:
+        return int(self.info.n_tokens)
+
+    @property
+    def handle(self) -> C.c_void_p:
+        if self._h is None:
+            raise RuntimeError("corpus was closed")
+        return self._h
+
+    def workspace(self) -> C.c_void_p:
+        """Default per-corpus scratch (single-threaded use, like the reference Searcher)."""
+        if self._ws is None:
+            ws = C.c_void_p()
+            _cabi.check(_cabi.lib().flmr_workspace_create(self.handle, 64, 1024, C.byref(ws)))
+            self._ws = ws
+        return self._ws
+
+    def close(self) -> None:
+        L = _cabi.lib()
+        if self._ws is not None:
+            L.flmr_workspace_destroy(self._ws)
+            self._ws = None
+        if self._h is not None:
+            torch.cuda.synchronize(self.device)
+            L.flmr_corpus_destroy(self._h)
+            self._h = None
+        self._keepalive = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __repr__(self) -> str:
+        i = self.info
+        return ("FlatCorpus(n_passages=%d, n_tokens=%d, device=%s, pid_base=%d, n_ctas=%d, adopted=%d)"
+                % (i.n_passages, i.n_tokens, self.device, i.pid_base, i.n_ctas, i.adopted))

@@ -1,0 +1,830 @@
+// flmr_maxsim.cu — C-ABI implementation (include/flmr_maxsim.h) of the B200-native FLMR/ColBERT
+// MaxSim + top-k path.  Host logic: corpus residency + partition metadata, query staging, pass
+// planning, launches.  Device code: the fused scan kernel (flmr_scan_kernel.cuh) plus four small
+// helper kernels (query staging, candidate merge, corpus repack, SIMT cross-check).
+//
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC
+// No libcuda link dependency: cuTensorMapEncodeTiled is resolved through the runtime's
+// cudaGetDriverEntryPoint, so the library loads (and its symbols can be checked) without a GPU.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <limits>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/flmr_maxsim.h"
+#include "flmr_scan_kernel.cuh"
+
+namespace {
+
+using namespace flmr;
+
+constexpr int kTileN = 128;  // passage tokens per streamed tile
+
+static_assert(kMaxK == FLMR_MAX_K, "header / kernel top-k capacity mismatch");
+static_assert(kGroup == FLMR_TOKEN_GROUP, "header / kernel token group mismatch");
+static_assert(kDim == FLMR_DIM, "header / kernel dim mismatch");
+
+// ---- error plumbing -----------------------------------------------------------------------------
+thread_local std::string g_last_error;
+thread_local int64_t g_launches = 0;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return code;
+}
+
+#define FLMR_CUDA(expr)                                                                     \
+  do {                                                                                      \
+    cudaError_t e__ = (expr);                                                               \
+    if (e__ != cudaSuccess)                                                                 \
+      return fail(e__ == cudaErrorMemoryAllocation ? FLMR_ERR_OOM : FLMR_ERR_CUDA,          \
+                  "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+  } while (0)
+
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = false;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) return;
+    ok = (cudaSetDevice(dev) == cudaSuccess);
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+// ---- TMA descriptor encoding through the runtime-resolved driver entry point ------------------------
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                   const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int get_encode_fn(EncodeTiledFn* out) {
+  static EncodeTiledFn fn = nullptr;
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lock(mu);
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    FLMR_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres));
+    if (qres != cudaDriverEntryPointSuccess || !p)
+      return fail(FLMR_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  *out = fn;
+  return FLMR_OK;
+}
+
+// bf16 [rows, 128] row-major matrix, box = 64 columns (128 B, one swizzle span) x box_rows rows.
+int encode_rows_map(CUtensorMap* map, const void* base, uint64_t rows, uint32_t box_rows) {
+  EncodeTiledFn enc = nullptr;
+  int rc = get_encode_fn(&enc);
+  if (rc) return rc;
+  const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(kDim), static_cast<cuuint64_t>(rows)};
+  const cuuint64_t gstride[1] = {static_cast<cuuint64_t>(kDim) * 2};
+  const cuuint32_t box[2] = {64u, box_rows};
+  const cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride,
+                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(FLMR_ERR_CUDA, "cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);
+  return FLMR_OK;
+}
+
+// ---- helper kernels --------------------------------------------------------------------------------
+
+// Stage the resident queries of one pass: each query padded with zero rows to rbq*32 rows, the whole
+// block padded with zero rows to n_mtiles*128 rows.  One thread per 16 bytes.
+__global__ void flmr_stage_queries_kernel(const uint4* __restrict__ q, uint4* __restrict__ qpad,
+                                          int nq_pass, int nq_total_rows, int row0, int rows_slice,
+                                          int rbq, int n_rows_pad) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int r = idx >> 4, c = idx & 15;
+  if (r >= n_rows_pad) return;
+  const int rows_q = rbq * 32;
+  const int b = r / rows_q, i = r % rows_q;
+  uint4 v = make_uint4(0u, 0u, 0u, 0u);
+  if (b < nq_pass && i < rows_slice)
+    v = q[(static_cast<int64_t>(b) * nq_total_rows + row0 + i) * 16 + c];
+  qpad[idx] = v;
+}
+
+// Copy passages into the padded layout: passage p occupies rows [poff[p], poff[p+1]) of dst, its
+// last token repeated over the padding rows.  One warp per passage, 2 rows per iteration.
+__global__ void flmr_repack_kernel(const uint4* __restrict__ src, const int64_t* __restrict__ soff,
+                                   const int64_t* __restrict__ poff, uint4* __restrict__ dst,
+                                   int64_t p_begin, int64_t p_count, int64_t src_row_base) {
+  const int64_t w = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= p_count) return;
+  const int64_t p = p_begin + w;
+  const int64_t s0 = soff[p], len = soff[p + 1] - s0;
+  const int64_t d0 = poff[p], plen = poff[p + 1] - d0;
+  const int half = lane >> 4, c = lane & 15;
+  for (int64_t j = half; j < plen; j += 2) {
+    const int64_t sj = j < len ? j : len - 1;
+    dst[(d0 + j) * 16 + c] = src[(s0 - src_row_base + sj) * 16 + c];
+  }
+}
+
+// Independent plain-SIMT MaxSim (test infrastructure): one block per (passage, query), one thread
+// per query token (looping if nq > blockDim), fp32 FMA over bf16 inputs, fixed-order block sum.
+__global__ void flmr_simt_maxsim_kernel(const __nv_bfloat16* __restrict__ d, const int64_t* poff,
+                                        const int32_t* doclen, const __nv_bfloat16* __restrict__ q,
+                                        int nq, float init, float* __restrict__ out,
+                                        int64_t n_passages) {
+  __shared__ float drow[kDim];
+  __shared__ float red[256];
+  const int64_t p = blockIdx.x;
+  const int b = blockIdx.y;
+  const int len = doclen[p];
+  const __nv_bfloat16* dp = d + poff[p] * kDim;
+  float total = 0.f;
+  for (int i0 = 0; i0 < nq; i0 += blockDim.x) {
+    const int i = i0 + threadIdx.x;
+    float m = init;
+    const __nv_bfloat16* qi = q + (static_cast<int64_t>(b) * nq + (i < nq ? i : 0)) * kDim;
+    for (int j = 0; j < len; ++j) {
+      __syncthreads();
+      if (threadIdx.x < kDim) drow[threadIdx.x] = __bfloat162float(dp[j * kDim + threadIdx.x]);
+      __syncthreads();
+      float acc = 0.f;
+#pragma unroll 16
+      for (int c = 0; c < kDim; ++c) acc = fmaf(__bfloat162float(qi[c]), drow[c], acc);
+      m = fmaxf(m, acc);
+    }
+    if (i < nq) total += m;
+  }
+  red[threadIdx.x] = total;
+  __syncthreads();
+  for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+    if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[static_cast<int64_t>(b) * n_passages + p] = red[0];
+}
+
+// Candidate merge: per query, select the k_out best of n candidates by (score desc, pid asc).
+// Candidates come either as packed keys written by the scan kernel (keys != null; pid = pid_base +
+// ~low32) or as (score, pid) arrays laid out [list][query][k_in].  One 1024-thread block per query,
+// up to kMergePer candidates per thread in registers, k_out selection rounds.
+constexpr int kMergeThreads = 1024;
+constexpr int kMergePer = 20;
+constexpr int64_t kPidEmpty = 0x7fffffffffffffffll;
+
+struct Cand {
+  uint32_t ord;  // ordered score; 0 = empty
+  int64_t pid;
+};
+__device__ __forceinline__ bool cand_better(const Cand& a, const Cand& b) {
+  return a.ord > b.ord || (a.ord == b.ord && a.pid < b.pid);
+}
+
+__global__ void __launch_bounds__(kMergeThreads)
+flmr_merge_kernel(const uint64_t* __restrict__ keys, const float* __restrict__ in_scores,
+                  const int64_t* __restrict__ in_pids, int n_lists, int n_queries, int k_in,
+                  int k_out, int64_t pid_base, float* __restrict__ out_scores,
+                  int64_t* __restrict__ out_pids) {
+  __shared__ uint32_t s_ord[32];
+  __shared__ int64_t s_pid[32];
+  __shared__ uint32_t w_ord;
+  __shared__ int64_t w_pid;
+  const int b = blockIdx.x;
+  const int n = n_lists * k_in;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  Cand c[kMergePer];
+#pragma unroll
+  for (int i = 0; i < kMergePer; ++i) {
+    const int idx = threadIdx.x + i * kMergeThreads;
+    c[i].ord = 0u;
+    c[i].pid = kPidEmpty;
+    if (idx < n) {
+      const int l = idx / k_in, j = idx % k_in;
+      const int64_t g = (static_cast<int64_t>(l) * n_queries + b) * k_in + j;
+      if (keys) {
+        const uint64_t key = keys[g];
+        if (key != 0ull) {
+          c[i].ord = static_cast<uint32_t>(key >> 32);
+          c[i].pid = pid_base + (0xFFFFFFFFu - static_cast<uint32_t>(key));
+        }
+      } else {
+        const int64_t pid = in_pids[g];
+        if (pid >= 0) {
+          c[i].ord = float_to_ordered(in_scores[g]);
+          c[i].pid = pid;
+        }
+      }
+    }
+  }
+  for (int r = 0; r < k_out; ++r) {
+    Cand best = c[0];
+#pragma unroll
+    for (int i = 1; i < kMergePer; ++i)
+      if (cand_better(c[i], best)) best = c[i];
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+      Cand o;
+      o.ord = __shfl_xor_sync(0xffffffffu, best.ord, off);
+      o.pid = __shfl_xor_sync(0xffffffffu, best.pid, off);
+      if (cand_better(o, best)) best = o;
+    }
+    if (lane == 0) {
+      s_ord[warp] = best.ord;
+      s_pid[warp] = best.pid;
+    }
+    __syncthreads();
+    if (warp == 0) {
+      Cand x;
+      x.ord = s_ord[lane];
+      x.pid = s_pid[lane];
+#pragma unroll
+      for (int off = 16; off >= 1; off >>= 1) {
+        Cand o;
+        o.ord = __shfl_xor_sync(0xffffffffu, x.ord, off);
+        o.pid = __shfl_xor_sync(0xffffffffu, x.pid, off);
+        if (cand_better(o, x)) x = o;
+      }
+      if (lane == 0) {
+        w_ord = x.ord;
+        w_pid = x.pid;
+        const bool empty = (x.ord == 0u);
+        out_scores[static_cast<int64_t>(b) * k_out + r] =
+            empty ? -INFINITY : ordered_to_float(x.ord);
+        out_pids[static_cast<int64_t>(b) * k_out + r] = empty ? -1 : x.pid;
+      }
+    }
+    __syncthreads();
+    const uint32_t wo = w_ord;
+    const int64_t wp = w_pid;
+    if (wo != 0u) {
+#pragma unroll
+      for (int i = 0; i < kMergePer; ++i)
+        if (c[i].ord == wo && c[i].pid == wp) {
+          c[i].ord = 0u;
+          c[i].pid = kPidEmpty;
+        }
+    }
+    // (w_ord/w_pid are rewritten only after the next round's first __syncthreads)
+  }
+}
+
+}  // namespace
+
+// ---- handles -----------------------------------------------------------------------------------------
+struct flmr_corpus {
+  int device = 0;
+  int64_t n_passages = 0, n_tokens = 0, n_rows = 0, pid_base = 0;
+  int n_ctas = 0;
+  int64_t n_tiles = 0;
+  bool adopted = false;
+  int64_t hbm_bytes = 0;
+  __nv_bfloat16* d_tokens = nullptr;   // [n_rows, 128] padded layout
+  int64_t* d_poff = nullptr;           // [n_passages + 1] stored-row offsets
+  int32_t* d_doclen = nullptr;         // [n_passages] real lengths
+  int32_t* d_cta_row_begin = nullptr;  // [n_ctas + 1]
+  int64_t* d_cta_tile_base = nullptr;  // [n_ctas + 1]
+  uint64_t* d_tile_end_mask = nullptr; // [n_tiles]
+  int32_t* d_tile_first_pid = nullptr; // [n_tiles]
+  CUtensorMap tmap_d;
+};
+
+struct flmr_workspace {
+  const flmr_corpus* corpus = nullptr;
+  int device = 0;
+  int max_queries = 0, max_nq = 0;
+  __nv_bfloat16* d_qpad = nullptr;     // [kMtMax*128, 128]
+  uint64_t* d_cand_keys = nullptr;     // [n_ctas][kNqMax][kMaxK]
+  float* d_acc = nullptr;              // [n_passages] lazily allocated (row-sliced queries)
+  int* h_status = nullptr;             // pinned + mapped: readable by the host even after a device trap
+  int* d_status = nullptr;             // device alias of h_status
+  CUtensorMap tmap_q;
+};
+
+namespace {
+
+thread_local bool g_profiling = false;
+struct EventPair {
+  cudaEvent_t a, b;
+};
+thread_local std::vector<EventPair> g_scan_events;
+
+template <typename T>
+int dev_upload(T** dptr, const std::vector<T>& h, int64_t* bytes_acc) {
+  const size_t bytes = std::max<size_t>(h.size(), 1) * sizeof(T);
+  FLMR_CUDA(cudaMalloc(reinterpret_cast<void**>(dptr), bytes));
+  if (!h.empty()) FLMR_CUDA(cudaMemcpy(*dptr, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+  if (bytes_acc) *bytes_acc += static_cast<int64_t>(bytes);
+  return FLMR_OK;
+}
+
+// Token-balanced split of the passages into n_ctas contiguous ranges + per-tile metadata.
+void build_partition(const std::vector<int64_t>& poff, int n_ctas, int tile_n,
+                     std::vector<int32_t>* cta_row_begin, std::vector<int64_t>* cta_tile_base,
+                     std::vector<uint64_t>* tile_end_mask, std::vector<int32_t>* tile_first_pid) {
+  const int64_t n = static_cast<int64_t>(poff.size()) - 1;
+  const int64_t rows = poff[n];
+  std::vector<int64_t> pbeg(n_ctas + 1);
+  pbeg[0] = 0;
+  for (int c = 1; c < n_ctas; ++c) {
+    const int64_t target = rows * c / n_ctas;
+    int64_t p = std::lower_bound(poff.begin(), poff.end(), target) - poff.begin();
+    p = std::min<int64_t>(std::max<int64_t>(p, pbeg[c - 1]), n);
+    pbeg[c] = p;
+  }
+  pbeg[n_ctas] = n;
+  cta_row_begin->resize(n_ctas + 1);
+  cta_tile_base->resize(n_ctas + 1);
+  int64_t tiles = 0;
+  for (int c = 0; c <= n_ctas; ++c) {
+    (*cta_row_begin)[c] = static_cast<int32_t>(poff[pbeg[c]]);
+    (*cta_tile_base)[c] = tiles;
+    if (c < n_ctas) tiles += (poff[pbeg[c + 1]] - poff[pbeg[c]] + tile_n - 1) / tile_n;
+  }
+  tile_end_mask->assign(tiles, 0ull);
+  tile_first_pid->assign(tiles, 0);
+  for (int c = 0; c < n_ctas; ++c) {
+    const int64_t r0 = poff[pbeg[c]];
+    const int64_t tb = (*cta_tile_base)[c];
+    const int64_t nt = (*cta_tile_base)[c + 1] - tb;
+    std::vector<char> seen(nt, 0);
+    for (int64_t p = pbeg[c]; p < pbeg[c + 1]; ++p) {
+      const int64_t last = poff[p + 1] - 1 - r0;  // last stored row of p, relative to the CTA
+      const int64_t t = last / tile_n;
+      const int g = static_cast<int>((last % tile_n) / kGroup);
+      (*tile_end_mask)[tb + t] |= (1ull << g);
+      if (!seen[t]) {
+        seen[t] = 1;
+        (*tile_first_pid)[tb + t] = static_cast<int32_t>(p);
+      }
+    }
+  }
+}
+
+int launch_scan(const flmr_corpus* c, flmr_workspace* ws, const ScanParams& p, cudaStream_t st) {
+  static bool attr_set[64] = {};
+  auto kern = flmr_scan_kernel<kTileN>;
+  if (c->device < 64 && !attr_set[c->device]) {
+    FLMR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   ScanCfg<kTileN>::kSmemBytes));
+    attr_set[c->device] = true;
+  }
+  EventPair ev{};
+  if (g_profiling) {
+    FLMR_CUDA(cudaEventCreate(&ev.a));
+    FLMR_CUDA(cudaEventCreate(&ev.b));
+    FLMR_CUDA(cudaEventRecord(ev.a, st));
+  }
+  kern<<<c->n_ctas, kScanThreads, ScanCfg<kTileN>::kSmemBytes, st>>>(ws->tmap_q, c->tmap_d, p);
+  FLMR_CUDA(cudaGetLastError());
+  ++g_launches;
+  if (g_profiling) {
+    FLMR_CUDA(cudaEventRecord(ev.b, st));
+    g_scan_events.push_back(ev);
+  }
+  return FLMR_OK;
+}
+
+int stage_queries(flmr_workspace* ws, const void* d_q, int64_t q_first, int nq_pass, int nq,
+                  int row0, int rows_slice, int rbq, int n_mtiles, cudaStream_t st) {
+  const int n_rows_pad = n_mtiles * kTileM;
+  const int threads = 256;
+  const int total = n_rows_pad * 16;
+  const uint4* src = reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(d_q) +
+                                                    q_first * nq * kDim);
+  flmr_stage_queries_kernel<<<(total + threads - 1) / threads, threads, 0, st>>>(
+      src, reinterpret_cast<uint4*>(ws->d_qpad), nq_pass, nq, row0, rows_slice, rbq, n_rows_pad);
+  FLMR_CUDA(cudaGetLastError());
+  ++g_launches;
+  return FLMR_OK;
+}
+
+int launch_merge_keys(const flmr_corpus* c, flmr_workspace* ws, int nq_pass, int k,
+                      float* d_out_scores, int64_t* d_out_pids, cudaStream_t st) {
+  if (static_cast<int64_t>(c->n_ctas) * k > kMergeThreads * kMergePer)
+    return fail(FLMR_ERR_UNSUPPORTED, "n_ctas*k = %lld exceeds merge capacity %d",
+                (long long)c->n_ctas * k, kMergeThreads * kMergePer);
+  flmr_merge_kernel<<<nq_pass, kMergeThreads, 0, st>>>(ws->d_cand_keys, nullptr, nullptr, c->n_ctas,
+                                                       nq_pass, k, k, c->pid_base, d_out_scores,
+                                                       d_out_pids);
+  FLMR_CUDA(cudaGetLastError());
+  ++g_launches;
+  return FLMR_OK;
+}
+
+// Shared driver of flmr_maxsim_scores / flmr_maxsim_topk.
+int run_search(const flmr_corpus* c, flmr_workspace* ws, const void* d_q, int n_queries, int nq,
+               unsigned flags, int k, float* d_all_scores, float* d_topk_scores,
+               int64_t* d_topk_pids, cudaStream_t st) {
+  if (!c || !ws || !d_q) return fail(FLMR_ERR_INVALID_ARG, "null corpus / workspace / query pointer");
+  if (ws->corpus != c) return fail(FLMR_ERR_INVALID_ARG, "workspace belongs to a different corpus");
+  if (n_queries < 0 || nq <= 0) return fail(FLMR_ERR_INVALID_ARG, "bad n_queries=%d nq=%d", n_queries, nq);
+  if (k < 0 || k > kMaxK) return fail(FLMR_ERR_UNSUPPORTED, "k=%d outside [1, %d]", k, kMaxK);
+  if (n_queries == 0) return FLMR_OK;
+  DeviceGuard guard(c->device);
+  if (!guard.ok) return fail(FLMR_ERR_CUDA, "cudaSetDevice(%d) failed", c->device);
+
+  ScanParams p{};
+  p.cta_row_begin = c->d_cta_row_begin;
+  p.cta_tile_base = c->d_cta_tile_base;
+  p.tile_end_mask = c->d_tile_end_mask;
+  p.tile_first_pid = c->d_tile_first_pid;
+  p.init_val = (flags & FLMR_FLAG_RELU) ? 0.f : -INFINITY;
+  p.n_passages = c->n_passages;
+  p.cand_keys = ws->d_cand_keys;
+  p.status = ws->d_status;
+  p.timeout_ns = 4000000000ull;
+  if (const char* e = getenv("FLMR_WATCHDOG_MS")) p.timeout_ns = strtoull(e, nullptr, 10) * 1000000ull;
+
+  const int rbq_total = (nq + 31) / 32;
+  int rc;
+  if (rbq_total <= kRbMax) {
+    // whole queries resident: as many queries per corpus pass as fit kRbMax 32-row blocks
+    const int qpp = std::min(kNqMax, kRbMax / rbq_total);
+    for (int b0 = 0; b0 < n_queries; b0 += qpp) {
+      const int nqp = std::min(qpp, n_queries - b0);
+      const int n_mtiles = (nqp * rbq_total * 32 + kTileM - 1) / kTileM;
+      if ((rc = stage_queries(ws, d_q, b0, nqp, nq, 0, nq, rbq_total, n_mtiles, st))) return rc;
+      p.n_mtiles = n_mtiles;
+      p.nq_pass = nqp;
+      p.rbq = rbq_total;
+      p.acc_in = nullptr;
+      p.acc_out = d_all_scores ? d_all_scores + static_cast<int64_t>(b0) * c->n_passages : nullptr;
+      p.k = k;
+      if ((rc = launch_scan(c, ws, p, st))) return rc;
+      if (k > 0 &&
+          (rc = launch_merge_keys(c, ws, nqp, k, d_topk_scores + static_cast<int64_t>(b0) * k,
+                                  d_topk_pids + static_cast<int64_t>(b0) * k, st)))
+        return rc;
+    }
+  } else {
+    // one query at a time, its rows sliced over several corpus passes; partial scores go through HBM
+    const int rows_per_slice = kRbMax * 32;
+    const int n_slices = (nq + rows_per_slice - 1) / rows_per_slice;
+    if (!d_all_scores && !ws->d_acc)
+      FLMR_CUDA(cudaMalloc(reinterpret_cast<void**>(&ws->d_acc),
+                           static_cast<size_t>(std::max<int64_t>(c->n_passages, 1)) * sizeof(float)));
+    for (int b = 0; b < n_queries; ++b) {
+      float* acc = d_all_scores ? d_all_scores + static_cast<int64_t>(b) * c->n_passages : ws->d_acc;
+      for (int s = 0; s < n_slices; ++s) {
+        const int row0 = s * rows_per_slice;
+        const int rows = std::min(rows_per_slice, nq - row0);
+        const int rbq = (rows + 31) / 32;
+        const int n_mtiles = (rbq * 32 + kTileM - 1) / kTileM;
+        const bool last = (s == n_slices - 1);
+        if ((rc = stage_queries(ws, d_q, b, 1, nq, row0, rows, rbq, n_mtiles, st))) return rc;
+        p.n_mtiles = n_mtiles;
+        p.nq_pass = 1;
+        p.rbq = rbq;
+        p.acc_in = (s == 0) ? nullptr : acc;
+        p.acc_out = (last && !d_all_scores) ? nullptr : acc;
+        p.k = last ? k : 0;
+        if ((rc = launch_scan(c, ws, p, st))) return rc;
+      }
+      if (k > 0 && (rc = launch_merge_keys(c, ws, 1, k, d_topk_scores + static_cast<int64_t>(b) * k,
+                                           d_topk_pids + static_cast<int64_t>(b) * k, st)))
+        return rc;
+    }
+  }
+  return FLMR_OK;
+}
+
+}  // namespace
+
+// =================================== C ABI =============================================================
+extern "C" {
+
+const char* flmr_last_error(void) { return g_last_error.c_str(); }
+int flmr_abi_version(void) { return FLMR_ABI_VERSION; }
+
+int flmr_corpus_create(const void* tokens, const int32_t* h_doclens, int64_t n_passages, int dim,
+                       int device, int64_t pid_base, unsigned flags, flmr_corpus_t** out) {
+  if (!out) return fail(FLMR_ERR_INVALID_ARG, "out is null");
+  *out = nullptr;
+  if (dim != kDim) return fail(FLMR_ERR_UNSUPPORTED, "dim=%d (only %d is supported)", dim, kDim);
+  if (n_passages <= 0 || !tokens || !h_doclens)
+    return fail(FLMR_ERR_INVALID_ARG, "empty corpus or null tokens/doclens");
+  std::vector<int64_t> soff(n_passages + 1), poff(n_passages + 1);
+  soff[0] = poff[0] = 0;
+  bool aligned = true;
+  for (int64_t p = 0; p < n_passages; ++p) {
+    const int32_t len = h_doclens[p];
+    if (len < 1)
+      return fail(FLMR_ERR_INVALID_ARG,
+                  "passage %lld has length %d; zero-length passages have no defined MaxSim score",
+                  (long long)p, len);
+    soff[p + 1] = soff[p] + len;
+    poff[p + 1] = poff[p] + (len + kGroup - 1) / kGroup * kGroup;
+    aligned &= (len % kGroup == 0);
+  }
+  const int64_t n_rows = poff[n_passages];
+  if (n_rows + kTileN >= (1ll << 31))
+    return fail(FLMR_ERR_UNSUPPORTED, "%lld stored token rows exceed the 2^31 per-shard limit; shard the corpus",
+                (long long)n_rows);
+
+  DeviceGuard guard(device);
+  if (!guard.ok) return fail(FLMR_ERR_CUDA, "cudaSetDevice(%d) failed", device);
+  cudaDeviceProp prop;
+  FLMR_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail(FLMR_ERR_UNSUPPORTED, "device %d is sm_%d%d; this library is sm_100a only", device,
+                prop.major, prop.minor);
+
+  cudaPointerAttributes attr{};
+  const bool is_device_ptr = (cudaPointerGetAttributes(&attr, tokens) == cudaSuccess) &&
+                             (attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged);
+  cudaGetLastError();
+  if ((flags & FLMR_CORPUS_ADOPT) && !is_device_ptr)
+    return fail(FLMR_ERR_INVALID_ARG, "FLMR_CORPUS_ADOPT requires a device pointer");
+  if (is_device_ptr && attr.type == cudaMemoryTypeDevice && attr.device != device)
+    return fail(FLMR_ERR_INVALID_ARG, "token matrix lives on device %d, corpus requested on %d",
+                attr.device, device);
+
+  flmr_corpus* c = new (std::nothrow) flmr_corpus();
+  if (!c) return fail(FLMR_ERR_OOM, "host allocation failed");
+  c->device = device;
+  c->n_passages = n_passages;
+  c->n_tokens = soff[n_passages];
+  c->n_rows = n_rows;
+  c->pid_base = pid_base;
+  int rc = FLMR_OK;
+  auto bail = [&](int code) {
+    flmr_corpus_destroy(c);
+    return code;
+  };
+
+  // --- token matrix residency ---
+  if ((flags & FLMR_CORPUS_ADOPT) && aligned &&
+      (reinterpret_cast<uintptr_t>(tokens) % 16 == 0)) {
+    c->d_tokens = static_cast<__nv_bfloat16*>(const_cast<void*>(tokens));
+    c->adopted = true;
+  } else {
+    const size_t bytes = static_cast<size_t>(n_rows) * kDim * 2;
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&c->d_tokens), bytes);
+    if (e != cudaSuccess)
+      return bail(fail(FLMR_ERR_OOM, "cudaMalloc(%zu B) for the token matrix failed: %s", bytes,
+                       cudaGetErrorString(e)));
+    c->hbm_bytes += static_cast<int64_t>(bytes);
+    int64_t *d_soff = nullptr, *d_poff_tmp = nullptr;
+    if ((rc = dev_upload(&d_soff, soff, nullptr))) return bail(rc);
+    if ((rc = dev_upload(&d_poff_tmp, poff, nullptr))) {
+      cudaFree(d_soff);
+      return bail(rc);
+    }
+    auto cleanup = [&]() {
+      cudaFree(d_soff);
+      cudaFree(d_poff_tmp);
+    };
+    if (is_device_ptr) {
+      const int threads = 256;
+      const int64_t blocks = (n_passages * 32 + threads - 1) / threads;
+      flmr_repack_kernel<<<static_cast<unsigned>(blocks), threads>>>(
+          static_cast<const uint4*>(tokens), d_soff, d_poff_tmp, reinterpret_cast<uint4*>(c->d_tokens),
+          0, n_passages, 0);
+      ++g_launches;
+      e = cudaGetLastError();
+      if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    } else {
+      // host source: stage through a bounded device buffer, chunk by chunk of whole passages
+      const int64_t chunk_rows = std::min<int64_t>(c->n_tokens, (256ll << 20) / (kDim * 2));
+      int64_t max_len = 0;
+      for (int64_t p = 0; p < n_passages; ++p) max_len = std::max<int64_t>(max_len, h_doclens[p]);
+      const int64_t buf_rows = std::max(chunk_rows, max_len);
+      uint4* d_stage = nullptr;
+      e = cudaMalloc(reinterpret_cast<void**>(&d_stage), static_cast<size_t>(buf_rows) * kDim * 2);
+      int64_t pa = 0;
+      while (e == cudaSuccess && pa < n_passages) {
+        int64_t pb = std::upper_bound(soff.begin() + pa, soff.end(), soff[pa] + buf_rows) - soff.begin() - 1;
+        pb = std::max(pb, pa + 1);
+        const int64_t rows = soff[pb] - soff[pa];
+        e = cudaMemcpy(d_stage, static_cast<const char*>(tokens) + soff[pa] * kDim * 2,
+                       static_cast<size_t>(rows) * kDim * 2, cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) break;
+        const int threads = 256;
+        const int64_t cnt = pb - pa;
+        const int64_t blocks = (cnt * 32 + threads - 1) / threads;
+        flmr_repack_kernel<<<static_cast<unsigned>(blocks), threads>>>(
+            d_stage, d_soff, d_poff_tmp, reinterpret_cast<uint4*>(c->d_tokens), pa, cnt, soff[pa]);
+        ++g_launches;
+        e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaDeviceSynchronize();
+        pa = pb;
+      }
+      cudaFree(d_stage);
+    }
+    cleanup();
+    if (e != cudaSuccess)
+      return bail(fail(FLMR_ERR_CUDA, "corpus repack failed: %s", cudaGetErrorString(e)));
+  }
+
+  // --- offsets / lengths (SIMT cross-check kernel, info) ---
+  {
+    std::vector<int32_t> lens(h_doclens, h_doclens + n_passages);
+    if ((rc = dev_upload(&c->d_poff, poff, &c->hbm_bytes))) return bail(rc);
+    if ((rc = dev_upload(&c->d_doclen, lens, &c->hbm_bytes))) return bail(rc);
+  }
+
+  // --- partition + tile metadata ---
+  int n_ctas = prop.multiProcessorCount;
+  if (const char* e = getenv("FLMR_NUM_CTAS")) n_ctas = std::max(1, atoi(e));
+  n_ctas = static_cast<int>(std::min<int64_t>(n_ctas, n_passages));
+  c->n_ctas = n_ctas;
+  {
+    std::vector<int32_t> row_begin, first_pid;
+    std::vector<int64_t> tile_base;
+    std::vector<uint64_t> end_mask;
+    build_partition(poff, n_ctas, kTileN, &row_begin, &tile_base, &end_mask, &first_pid);
+    c->n_tiles = static_cast<int64_t>(end_mask.size());
+    if ((rc = dev_upload(&c->d_cta_row_begin, row_begin, &c->hbm_bytes))) return bail(rc);
+    if ((rc = dev_upload(&c->d_cta_tile_base, tile_base, &c->hbm_bytes))) return bail(rc);
+    if ((rc = dev_upload(&c->d_tile_end_mask, end_mask, &c->hbm_bytes))) return bail(rc);
+    if ((rc = dev_upload(&c->d_tile_first_pid, first_pid, &c->hbm_bytes))) return bail(rc);
+  }
+  if ((rc = encode_rows_map(&c->tmap_d, c->d_tokens, static_cast<uint64_t>(n_rows), kTileN)))
+    return bail(rc);
+  *out = c;
+  return FLMR_OK;
+}
+
+int flmr_corpus_destroy(flmr_corpus_t* c) {
+  if (!c) return FLMR_OK;
+  DeviceGuard guard(c->device);
+  if (!c->adopted && c->d_tokens) cudaFree(c->d_tokens);
+  cudaFree(c->d_poff);
+  cudaFree(c->d_doclen);
+  cudaFree(c->d_cta_row_begin);
+  cudaFree(c->d_cta_tile_base);
+  cudaFree(c->d_tile_end_mask);
+  cudaFree(c->d_tile_first_pid);
+  delete c;
+  return FLMR_OK;
+}
+
+int flmr_corpus_info(const flmr_corpus_t* c, flmr_corpus_info_t* out) {
+  if (!c || !out) return fail(FLMR_ERR_INVALID_ARG, "null argument");
+  out->n_passages = c->n_passages;
+  out->n_tokens = c->n_tokens;
+  out->n_rows = c->n_rows;
+  out->pid_base = c->pid_base;
+  out->dim = kDim;
+  out->device = c->device;
+  out->n_ctas = c->n_ctas;
+  out->adopted = c->adopted ? 1 : 0;
+  out->n_tiles = c->n_tiles;
+  out->hbm_bytes = c->hbm_bytes;
+  return FLMR_OK;
+}
+
+int flmr_workspace_create(const flmr_corpus_t* c, int max_queries, int max_nq,
+                          flmr_workspace_t** out) {
+  if (!c || !out) return fail(FLMR_ERR_INVALID_ARG, "null argument");
+  *out = nullptr;
+  DeviceGuard guard(c->device);
+  if (!guard.ok) return fail(FLMR_ERR_CUDA, "cudaSetDevice(%d) failed", c->device);
+  flmr_workspace* ws = new (std::nothrow) flmr_workspace();
+  if (!ws) return fail(FLMR_ERR_OOM, "host allocation failed");
+  ws->corpus = c;
+  ws->device = c->device;
+  ws->max_queries = max_queries;
+  ws->max_nq = max_nq;
+  auto bail = [&](int code) {
+    flmr_workspace_destroy(ws);
+    return code;
+  };
+  cudaError_t e;
+  const size_t qbytes = static_cast<size_t>(kMtMax) * kTileM * kDim * 2;
+  if ((e = cudaMalloc(reinterpret_cast<void**>(&ws->d_qpad), qbytes)) != cudaSuccess ||
+      (e = cudaMemset(ws->d_qpad, 0, qbytes)) != cudaSuccess ||
+      (e = cudaMalloc(reinterpret_cast<void**>(&ws->d_cand_keys),
+                      static_cast<size_t>(c->n_ctas) * kNqMax * kMaxK * 8)) != cudaSuccess ||
+      (e = cudaHostAlloc(reinterpret_cast<void**>(&ws->h_status), sizeof(int), cudaHostAllocMapped)) != cudaSuccess ||
+      (e = cudaHostGetDevicePointer(reinterpret_cast<void**>(&ws->d_status), ws->h_status, 0)) != cudaSuccess)
+    return bail(fail(FLMR_ERR_CUDA, "workspace allocation failed: %s", cudaGetErrorString(e)));
+  *ws->h_status = 0;
+  int rc = encode_rows_map(&ws->tmap_q, ws->d_qpad, static_cast<uint64_t>(kMtMax) * kTileM, kTileM);
+  if (rc) return bail(rc);
+  *out = ws;
+  return FLMR_OK;
+}
+
+int flmr_workspace_destroy(flmr_workspace_t* ws) {
+  if (!ws) return FLMR_OK;
+  DeviceGuard guard(ws->device);
+  cudaFree(ws->d_qpad);
+  cudaFree(ws->d_cand_keys);
+  cudaFree(ws->d_acc);
+  if (ws->h_status) cudaFreeHost(ws->h_status);
+  delete ws;
+  return FLMR_OK;
+}
+
+int flmr_workspace_status(const flmr_workspace_t* ws, int* out) {
+  if (!ws || !out) return fail(FLMR_ERR_INVALID_ARG, "null argument");
+  *out = ws->h_status ? *reinterpret_cast<volatile int*>(ws->h_status) : 0;
+  return FLMR_OK;
+}
+
+int flmr_maxsim_scores(const flmr_corpus_t* corpus, flmr_workspace_t* ws, const void* d_q,
+                       int n_queries, int nq, unsigned flags, float* d_out_scores, void* stream) {
+  if (!d_out_scores) return fail(FLMR_ERR_INVALID_ARG, "d_out_scores is null");
+  return run_search(corpus, ws, d_q, n_queries, nq, flags, 0, d_out_scores, nullptr, nullptr,
+                    static_cast<cudaStream_t>(stream));
+}
+
+int flmr_maxsim_topk(const flmr_corpus_t* corpus, flmr_workspace_t* ws, const void* d_q,
+                     int n_queries, int nq, int k, unsigned flags, float* d_out_scores,
+                     int64_t* d_out_pids, void* stream) {
+  if (!d_out_scores || !d_out_pids) return fail(FLMR_ERR_INVALID_ARG, "output pointer is null");
+  if (k < 1) return fail(FLMR_ERR_INVALID_ARG, "k=%d must be >= 1", k);
+  return run_search(corpus, ws, d_q, n_queries, nq, flags, k, nullptr, d_out_scores, d_out_pids,
+                    static_cast<cudaStream_t>(stream));
+}
+
+int flmr_topk_merge(const float* d_in_scores, const int64_t* d_in_pids, int n_lists, int n_queries,
+                    int k_in, int k_out, float* d_out_scores, int64_t* d_out_pids, int device,
+                    void* stream) {
+  if (!d_in_scores || !d_in_pids || !d_out_scores || !d_out_pids)
+    return fail(FLMR_ERR_INVALID_ARG, "null pointer");
+  if (n_lists < 1 || n_queries < 0 || k_in < 1 || k_out < 1 || k_out > kMaxK)
+    return fail(FLMR_ERR_INVALID_ARG, "bad merge shape n_lists=%d n_queries=%d k_in=%d k_out=%d",
+                n_lists, n_queries, k_in, k_out);
+  if (static_cast<int64_t>(n_lists) * k_in > kMergeThreads * kMergePer)
+    return fail(FLMR_ERR_UNSUPPORTED, "n_lists*k_in = %lld exceeds merge capacity %d",
+                (long long)n_lists * k_in, kMergeThreads * kMergePer);
+  if (n_queries == 0) return FLMR_OK;
+  DeviceGuard guard(device);
+  if (!guard.ok) return fail(FLMR_ERR_CUDA, "cudaSetDevice(%d) failed", device);
+  flmr_merge_kernel<<<n_queries, kMergeThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      nullptr, d_in_scores, d_in_pids, n_lists, n_queries, k_in, k_out, 0, d_out_scores, d_out_pids);
+  FLMR_CUDA(cudaGetLastError());
+  ++g_launches;
+  return FLMR_OK;
+}
+
+int flmr_debug_maxsim_scores_simt(const flmr_corpus_t* c, const void* d_q, int n_queries, int nq,
+                                  unsigned flags, float* d_out_scores, void* stream) {
+  if (!c || !d_q || !d_out_scores) return fail(FLMR_ERR_INVALID_ARG, "null argument");
+  if (n_queries <= 0 || nq <= 0) return fail(FLMR_ERR_INVALID_ARG, "bad shape");
+  if (c->n_passages > 0x7fffffffll || n_queries > 65535)
+    return fail(FLMR_ERR_UNSUPPORTED, "SIMT cross-check grid too large");
+  DeviceGuard guard(c->device);
+  if (!guard.ok) return fail(FLMR_ERR_CUDA, "cudaSetDevice(%d) failed", c->device);
+  const int threads = nq >= 256 ? 256 : (nq > 128 ? 256 : 128);
+  dim3 grid(static_cast<unsigned>(c->n_passages), static_cast<unsigned>(n_queries));
+  flmr_simt_maxsim_kernel<<<grid, threads, 0, static_cast<cudaStream_t>(stream)>>>(
+      c->d_tokens, c->d_poff, c->d_doclen, static_cast<const __nv_bfloat16*>(d_q), nq,
+      (flags & FLMR_FLAG_RELU) ? 0.f : -INFINITY, d_out_scores, c->n_passages);
+  FLMR_CUDA(cudaGetLastError());
+  ++g_launches;
+  return FLMR_OK;
+}
+
+int64_t flmr_launch_count(int reset) {
+  const int64_t v = g_launches;
+  if (reset) g_launches = 0;
+  return v;
+}
+
+int flmr_set_profiling(int enable) {
+  g_profiling = enable != 0;
+  return FLMR_OK;
+}
+
+int flmr_scan_kernel_stats(double* total_ms, int64_t* launches, int reset) {
+  double tot = 0.0;
+  int64_t n = 0;
+  for (auto& ev : g_scan_events) {
+    float ms = 0.f;
+    if (cudaEventSynchronize(ev.b) == cudaSuccess && cudaEventElapsedTime(&ms, ev.a, ev.b) == cudaSuccess) {
+      tot += ms;
+      ++n;
+    }
+  }
+  if (total_ms) *total_ms = tot;
+  if (launches) *launches = n;
+  if (reset) {
+    for (auto& ev : g_scan_events) {
+      cudaEventDestroy(ev.a);
+      cudaEventDestroy(ev.b);
+    }
+    g_scan_events.clear();
+  }
+  return FLMR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,88 @@
+"""Functional surface of the hot path: MaxSim scores and fused top-k over a resident corpus, plus
+drop-in equivalents of the reference's scoring functions (same names, argument meaning and error
+behaviour as third_party/ColBERT/colbert/modeling/colbert.py:235-311) that run on the CUDA path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import torch
+
+from . import _cabi
+from .corpus import FlatCorpus
+
+
+def _prep_queries(corpus: FlatCorpus, Q: torch.Tensor) -> torch.Tensor:
+    if Q.dim() == 2:
+        Q = Q.unsqueeze(0)
+    if Q.dim() != 3 or Q.size(-1) != _cabi.DIM:
+        raise ValueError("Q must be [n_queries, nq, %d], got %s" % (_cabi.DIM, tuple(Q.shape)))
+    return Q.detach().to(device=corpus.device, dtype=torch.bfloat16).contiguous()
+
+
+def _stream(corpus: FlatCorpus) -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream(corpus.device).cuda_stream)
+
+
+def maxsim_scores(corpus: FlatCorpus, Q: torch.Tensor, relu: bool = False,
+                  out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``out[b, p] = sum_i max_j <Q[b,i], D_p[j]>`` for every passage of the shard (fp32, on GPU)."""
+    Qd = _prep_queries(corpus, Q)
+    B, nq = Qd.size(0), Qd.size(1)
+    if out is None:
+        out = torch.empty((B, corpus.n_passages), dtype=torch.float32, device=corpus.device)
+    elif out.shape != (B, corpus.n_passages) or out.dtype != torch.float32 or not out.is_contiguous():
+        raise ValueError("out must be a contiguous fp32 [n_queries, n_passages] CUDA tensor")
+    with torch.cuda.device(corpus.device):
+        _cabi.check(_cabi.lib().flmr_maxsim_scores(
+            corpus.handle, corpus.workspace(), C.c_void_p(Qd.data_ptr()), B, nq,
+            _cabi.FLAG_RELU if relu else 0, C.c_void_p(out.data_ptr()), _stream(corpus)))
+    return out
+
+
+def maxsim_topk(corpus: FlatCorpus, Q: torch.Tensor, k: int, relu: bool = False
+                ) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Fused scan + top-k: ``(scores fp32 [B,k], pids int64 [B,k])`` sorted by descending score."""
+    if not 1 <= k <= _cabi.MAX_K:
+        raise ValueError("k=%d outside [1, %d]" % (k, _cabi.MAX_K))
+    Qd = _prep_queries(corpus, Q)
+    B, nq = Qd.size(0), Qd.size(1)
+    scores = torch.empty((B, k), dtype=torch.float32, device=corpus.device)
+    pids = torch.empty((B, k), dtype=torch.int64, device=corpus.device)
+    with torch.cuda.device(corpus.device):
+        _cabi.check(_cabi.lib().flmr_maxsim_topk(
+            corpus.handle, corpus.workspace(), C.c_void_p(Qd.data_ptr()), B, nq, k,
+            _cabi.FLAG_RELU if relu else 0, C.c_void_p(scores.data_ptr()),
+            C.c_void_p(pids.data_ptr()), _stream(corpus)))
+    return scores, pids
+
+
+def topk_merge(scores: torch.Tensor, pids: torch.Tensor, k_out: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Merge ``[n_lists, B, k_in]`` candidate lists into ``[B, k_out]`` (score desc, pid asc)."""
+    if scores.shape != pids.shape or scores.dim() != 3:
+        raise ValueError("scores/pids must both be [n_lists, n_queries, k_in]")
+    dev = scores.device
+    s = scores.detach().to(torch.float32).contiguous()
+    p = pids.detach().to(torch.int64).contiguous()
+    L_, B, k_in = s.shape
+    out_s = torch.empty((B, k_out), dtype=torch.float32, device=dev)
+    out_p = torch.empty((B, k_out), dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        _cabi.check(_cabi.lib().flmr_topk_merge(
+            C.c_void_p(s.data_ptr()), C.c_void_p(p.data_ptr()), L_, B, k_in, k_out,
+            C.c_void_p(out_s.data_ptr()), C.c_void_p(out_p.data_ptr()), int(dev.index),
+            C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+    return out_s, out_p
+
+
+def debug_scores_simt(corpus: FlatCorpus, Q: torch.Tensor, relu: bool = False) -> torch.Tensor:
+    """Test infrastructure: independent plain-SIMT fp32 kernel (same contract as maxsim_scores)."""
+    Qd = _prep_queries(corpus, Q)
+    B, nq = Qd.size(0), Qd.size(1)
+    out = torch.empty((B, corpus.n_passages), dtype=torch.float32, device=corpus.device)
+    with torch.cuda.device(corpus.device):
+        _cabi.check(_cabi.lib().flmr_debug_maxsim_scores_simt(
+            corpus.handle, C.c_void_p(Qd.data_ptr()), B, nq, _cabi.FLAG_RELU if relu else 0,
+            C.c_void_p(out.data_ptr()), _stream(corpus)))
+    return out
