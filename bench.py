@@ -1,0 +1,372 @@
+#!/usr/bin/env python
+"""bench.py — queries/sec of FLMR late-interaction MaxSim + top-k over a 1M-passage corpus.
+
+    python bench.py --gpus 1 --steps K --warmup W            # this repository's CUDA path
+    python bench.py --impl reference ...                     # the reference's CPU path (host cores)
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[2] / north_star): synthetic L2-normalised bf16 embeddings,
+N = 1,000,000 passages x Nd = 180 tokens x d = 128, queries of Nq = 320 tokens, k = 5.  At N GPUs the
+passage-token matrix is sharded by contiguous passage ranges (1M / N per GPU: STRONG scaling), each
+rank scans its shard, one NCCL all-gather of per-shard top-k, merge.
+
+One "step" = one call of the hot path on a batch of `--batch` queries.  `value` = whole-job
+queries/sec with the query batch already resident in HBM; `e2e` = the same through the
+reference-facing `Searcher._search_all_Q` with the query batch in pinned HOST memory and the ranking
+returned as Python lists (H2D + D2H inside the timed region).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "queries/sec MaxSim+top-k over 1M-passage corpus (Nq=320, Nd=180, d=128)"
+UNIT = "queries/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--passages", type=int, default=1_000_000)
+    ap.add_argument("--nd", type=int, default=180)
+    ap.add_argument("--nq", type=int, default=320)
+    ap.add_argument("--batch", type=int, default=16)
+    ap.add_argument("--k", type=int, default=5)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the baseline sample")
+    return ap.parse_args()
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"hbm_gbs": float(p["hbm_gbs"]), "bf16_burst": float(p["bf16_tflops"]),
+                "bf16_sustained": float(p.get("bf16_tflops_sustained", p["bf16_tflops"])), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_burst": 1590.0, "bf16_sustained": 1400.0, "source": "fallback"}
+
+
+# --------------------------------------------------------------------------------------------------
+# reference CPU leg (oracle/_ref when the reference's segmented_maxsim.cpp was compiled, else the
+# oracle port).  TEST/BASELINE INFRASTRUCTURE: never on the product path.
+# --------------------------------------------------------------------------------------------------
+def make_cpu_scorer():
+    """Returns (kind, fn(Q [nq,d] fp32 torch, D [T,d] fp32 torch, doclens int64 torch) -> scores [n])."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    try:
+        import build_ref
+        mod = build_ref.load()
+    except Exception:
+        mod = None
+    if mod is not None:
+        def ref_fn(Q, D, doclens):
+            # colbert_score_packed, CPU branch (third_party/ColBERT/colbert/modeling/colbert.py:304,311):
+            #   scores = D_packed @ Q.T ; ColBERT.segmented_maxsim(scores, D_lengths)
+            return mod.segmented_maxsim_cpp((D @ Q.T).contiguous(), doclens)
+        return "reference", ref_fn
+    from oracle import maxsim_oracle as O
+
+    def port_fn(Q, D, doclens):
+        return torch.from_numpy(O.colbert_score_packed(Q.numpy()[None], D.numpy(), doclens.numpy()))
+    return "port", port_fn
+
+
+def cpu_reference_rate(args, target_seconds, steps=1, warmup=0):
+    """queries/sec of the reference's exhaustive CPU MaxSim extrapolated to the full corpus from a
+    bounded sample of passages (the fp32 corpus would be 92 GB).  Returns dict for `cpu_baseline`."""
+    import torch
+    kind, fn = make_cpu_scorer()
+    cores = torch.get_num_threads()
+    g = torch.Generator().manual_seed(0)
+    Q = torch.nn.functional.normalize(torch.randn(args.nq, 128, generator=g), dim=-1).bfloat16().float()
+
+    def make(n):
+        D = torch.nn.functional.normalize(torch.randn(n * args.nd, 128, generator=g), dim=-1).bfloat16().float()
+        return D, torch.full((n,), args.nd, dtype=torch.int64)
+
+    n_probe = 2000
+    D, dl = make(n_probe)
+    fn(Q, D, dl)                                   # warm caches / thread pools
+    t0 = time.perf_counter()
+    fn(Q, D, dl)
+    t_probe = time.perf_counter() - t0
+    n_sample = int(min(max(n_probe, n_probe * target_seconds / max(t_probe, 1e-4)), 100_000, args.passages))
+    D, dl = make(n_sample)
+    for _ in range(warmup):
+        fn(Q, D, dl)
+    times = []
+    for _ in range(max(steps, 1)):
+        t0 = time.perf_counter()
+        s = fn(Q, D, dl)
+        s.topk(min(args.k, n_sample))
+        times.append(time.perf_counter() - t0)
+    t_step = sum(times) / len(times)
+    per_query_full = t_step * (args.passages / n_sample)
+    return {"value": 1.0 / per_query_full, "unit": UNIT, "cores": cores, "kind": kind,
+            "sample": "1 query x %d of %d passages (Nq=%d, Nd=%d) exhaustive colbert_score_packed + topk, "
+                      "%.2f s per step, linearly extrapolated to the full corpus" %
+                      (n_sample, args.passages, args.nq, args.nd, t_step),
+            "ms_per_step": t_step * 1e3}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    base = cpu_reference_rate(args, target_seconds=max(2.0, min(args.cpu_seconds, 20.0)),
+                              steps=args.steps, warmup=min(args.warmup, 1))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": base["ms_per_step"],
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "FLMR MaxSim top-%d, %d passages x Nd=%d, Nq=%d, d=128 (bounded CPU sample)"
+                               % (args.k, args.passages, args.nd, args.nq),
+                   "n_passages": args.passages, "nd": args.nd, "nq": args.nq, "k": args.k},
+        "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------
+# this repository's arm
+# --------------------------------------------------------------------------------------------------
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.QUERY,
+                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, smax, power, reasons = [], [], [], set()
+        for line in self.f.read().strip().splitlines():
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                smax.append(float(parts[2]))
+                power.append(float(parts[3]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"),
+                                 parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(smax), "power_w_max": max(power),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import ravqa_b200 as R
+    from ravqa_b200 import _cabi
+    import ctypes as C
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("--gpus %d needs torchrun with that many ranks" % args.gpus)
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    # ---- this rank's shard of the synthetic corpus, generated on-device ----
+    n_total, nd, nq, B, k = args.passages, args.nd, args.nq, args.batch, args.k
+    p0 = n_total * rank // world
+    p1 = n_total * (rank + 1) // world
+    n_local = p1 - p0
+    D = torch.empty((n_local * nd, 128), dtype=torch.bfloat16, device=dev)
+    chunk = 20_000
+    for c0 in range(0, n_local, chunk):
+        c1 = min(n_local, c0 + chunk)
+        g = torch.Generator(device=dev).manual_seed(1_000_003 * (p0 + c0) + 17)
+        x = torch.randn(((c1 - c0) * nd, 128), device=dev, generator=g)
+        D[c0 * nd:c1 * nd] = torch.nn.functional.normalize(x, dim=-1).to(torch.bfloat16)
+    del x
+    corpus = R.FlatCorpus(D, np.full(n_local, nd, dtype=np.int32), device=dev, pid_base=p0)
+    gq = torch.Generator().manual_seed(12345)
+    Q_host = torch.nn.functional.normalize(torch.randn((B, nq, 128), generator=gq), dim=-1).pin_memory()
+    Q_dev = Q_host.to(dev).to(torch.bfloat16)
+    sharded = R.ShardedSearcher.from_corpus(corpus)
+    L = _cabi.lib()
+
+    def step_device():
+        return sharded.search(Q_dev, k)
+
+    class _ShardedFacade(R.Searcher):
+        """Searcher whose tensor search goes through the sharded path (all-gather + merge)."""
+        def _search_tensors(self, Q, kk, filter_fn=None):
+            from ravqa_b200.maxsim import _prep_queries
+            return sharded.search(_prep_queries(corpus, Q), kk)
+
+    searcher = _ShardedFacade(index=corpus)
+    qids = list(range(B))
+
+    def step_e2e():
+        return searcher._search_all_Q(qids, Q_host, k, progress=False)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed(fn, steps, warmup, profile=False):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        if profile:
+            L.flmr_scan_kernel_stats(None, None, 1)
+            L.flmr_set_profiling(1)
+        L.flmr_launch_count(1)
+        sampler = ClockSampler(local_rank) if rank == 0 else None
+        if sampler:
+            sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        for _ in range(steps):
+            out = fn()
+        e1.record()
+        barrier()
+        wall_ms = (time.perf_counter() - t0) * 1e3
+        dev_ms = e0.elapsed_time(e1)
+        clocks = sampler.stop() if sampler else None
+        launches = int(L.flmr_launch_count(0))
+        scan_ms, scan_n = C.c_double(0), C.c_int64(0)
+        if profile:
+            L.flmr_scan_kernel_stats(C.byref(scan_ms), C.byref(scan_n), 1)
+            L.flmr_set_profiling(0)
+        t = torch.tensor([dev_ms, wall_ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return {"dev_ms": t[0].item(), "wall_ms": t[1].item(), "clocks": clocks, "launches": launches,
+                "scan_ms": scan_ms.value, "scan_n": scan_n.value, "out": out}
+
+    # device-resident timing (value) with per-launch scan-kernel events for the roofline
+    r_dev = timed(step_device, args.steps, args.warmup, profile=True)
+    ms_per_step = r_dev["dev_ms"] / args.steps
+    value = B * 1e3 / ms_per_step
+    # end-to-end through the reference-facing API with host buffers (wall clock spans H2D/D2H/lists)
+    r_e2e = timed(step_e2e, args.steps, min(args.warmup, 2))
+    e2e_ms = max(r_e2e["dev_ms"], r_e2e["wall_ms"]) / args.steps
+    e2e_value = B * 1e3 / e2e_ms
+
+    # sanity inside the bench: the fused result equals top-k of the all-scores path on this shard
+    s_all = R.maxsim_scores(corpus, Q_dev[:1])
+    ts, tp = R.maxsim_topk(corpus, Q_dev[:1], k)
+    rs, rp = torch.sort(s_all, dim=1, descending=True, stable=True)
+    self_check = bool(torch.equal(tp, rp[:, :k] + p0))
+
+    if rank == 0:
+        peaks = load_peaks()
+        info = corpus.info
+        # dominant kernel = flmr_scan_kernel: one launch scans this rank's shard for the queries resident
+        # in that pass.  Algorithmic work per launch (DESIGN.md "Roofline"):
+        q_per_launch = max(1, 12 // ((nq + 31) // 32)) if (nq + 31) // 32 <= 12 else 1
+        q_per_launch = min(q_per_launch, B)
+        flops_launch = 2.0 * q_per_launch * nq * 128 * float(info.n_tokens)
+        bytes_launch = float(info.n_tokens) * 256.0
+        scan_avg_ms = r_dev["scan_ms"] / max(r_dev["scan_n"], 1)
+        ach_tf = flops_launch / (scan_avg_ms * 1e-3) / 1e12 if scan_avg_ms > 0 else 0.0
+        ach_gbs = bytes_launch / (scan_avg_ms * 1e-3) / 1e9 if scan_avg_ms > 0 else 0.0
+        roofline = {
+            "bound": "tensor", "achieved": ach_tf, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
+            "frac": ach_tf / peaks["bf16_sustained"], "traffic": None,
+            "peak_source": peaks["source"] + " (sustained cuBLAS bf16: kernel timed inside a long step)",
+            "kernel": "flmr_scan_kernel<128>", "launch_ms": scan_avg_ms, "launches_timed": r_dev["scan_n"],
+            "scan_share_of_step": r_dev["scan_ms"] / r_dev["dev_ms"] if r_dev["dev_ms"] > 0 else None,
+            "hbm": {"achieved": ach_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                    "frac": ach_gbs / peaks["hbm_gbs"], "frac_of_8TBs": ach_gbs / 8000.0,
+                    "algorithmic_bytes_per_launch": bytes_launch},
+            "algorithmic_flops_per_launch": flops_launch,
+        }
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "FLMR MaxSim top-%d: %d passages x Nd=%d, Nq=%d, d=128, batch %d queries/step"
+                                   % (k, n_total, nd, nq, B),
+                       "n_passages": n_total, "nd": nd, "nq": nq, "dim": 128, "k": k, "batch": B,
+                       "parallelism": "passage-shard x%d + allgather(top-k)" % world,
+                       "l2": "inputs larger than L2 (%.1f GB of passage tokens per GPU per pass)"
+                             % (info.n_tokens * 256 / 1e9)},
+            "clocks": r_dev["clocks"],
+            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": B * nq * 128 * 4, "d2h_bytes_per_step": B * k * 12,
+                    "api": "Searcher._search_all_Q(queries, Q_host_fp32_pinned, k) -> Ranking"},
+            "gpu_launches": r_dev["launches"],
+            "roofline": roofline,
+            "self_check_fused_topk_equals_sorted_scores": self_check,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                base = cpu_reference_rate(args, args.cpu_seconds)
+                line["cpu_baseline"] = {kk: base[kk] for kk in ("value", "unit", "cores", "kind", "sample")}
+            except Exception as e:  # the baseline must never take the bench line down
+                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": None, "kind": "error", "sample": repr(e)}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -149,6 +149,15 @@ int flmr_topk_merge(const float* d_in_scores, const int64_t* d_in_pids, int n_li
 int flmr_debug_maxsim_scores_simt(const flmr_corpus_t* corpus, const void* d_q, int n_queries,
                                   int nq, unsigned flags, float* d_out_scores, void* stream);
 
+/* Test infrastructure, host-only (no GPU needed): the token-balanced CTA partition + per-tile
+ * passage-end metadata the scan kernel consumes, for `n_ctas` persistent CTAs and 128-token tiles.
+ * cta_row_begin / cta_tile_base hold min(n_ctas, n_passages) + 1 entries; tile arrays may be NULL
+ * to query *n_tiles_out only. */
+int flmr_debug_build_partition(const int32_t* h_doclens, int64_t n_passages, int n_ctas,
+                               int32_t* cta_row_begin, int64_t* cta_tile_base,
+                               uint64_t* tile_end_mask, int32_t* tile_first_pid,
+                               int64_t tile_capacity, int64_t* n_tiles_out);
+
 /* Kernels launched by this library on the calling thread since the last reset (bench evidence). */
 int64_t flmr_launch_count(int reset);
 

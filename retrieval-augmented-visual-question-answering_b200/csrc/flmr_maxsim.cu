@@ -449,6 +449,7 @@ int run_search(const flmr_corpus* c, flmr_workspace* ws, const void* d_q, int n_
   p.cand_keys = ws->d_cand_keys;
   p.status = ws->d_status;
   p.timeout_ns = 4000000000ull;
+  if (const char* e = getenv("FLMR_DEBUG_MODE")) p.debug_mode = atoi(e);
   if (const char* e = getenv("FLMR_WATCHDOG_MS")) p.timeout_ns = strtoull(e, nullptr, 10) * 1000000ull;
 
   const int rbq_total = (nq + 31) / 32;
@@ -791,6 +792,35 @@ int flmr_debug_maxsim_scores_simt(const flmr_corpus_t* c, const void* d_q, int n
       (flags & FLMR_FLAG_RELU) ? 0.f : -INFINITY, d_out_scores, c->n_passages);
   FLMR_CUDA(cudaGetLastError());
   ++g_launches;
+  return FLMR_OK;
+}
+
+int flmr_debug_build_partition(const int32_t* h_doclens, int64_t n_passages, int n_ctas,
+                               int32_t* cta_row_begin, int64_t* cta_tile_base,
+                               uint64_t* tile_end_mask, int32_t* tile_first_pid,
+                               int64_t tile_capacity, int64_t* n_tiles_out) {
+  if (!h_doclens || n_passages <= 0 || n_ctas < 1 || !cta_row_begin || !cta_tile_base || !n_tiles_out)
+    return fail(FLMR_ERR_INVALID_ARG, "bad argument");
+  std::vector<int64_t> poff(n_passages + 1);
+  poff[0] = 0;
+  for (int64_t p = 0; p < n_passages; ++p) {
+    if (h_doclens[p] < 1) return fail(FLMR_ERR_INVALID_ARG, "passage %lld has length %d", (long long)p, h_doclens[p]);
+    poff[p + 1] = poff[p] + (h_doclens[p] + kGroup - 1) / kGroup * kGroup;
+  }
+  n_ctas = static_cast<int>(std::min<int64_t>(n_ctas, n_passages));
+  std::vector<int32_t> rb, fp;
+  std::vector<int64_t> tb;
+  std::vector<uint64_t> em;
+  build_partition(poff, n_ctas, kTileN, &rb, &tb, &em, &fp);
+  *n_tiles_out = static_cast<int64_t>(em.size());
+  std::copy(rb.begin(), rb.end(), cta_row_begin);
+  std::copy(tb.begin(), tb.end(), cta_tile_base);
+  if (tile_end_mask && tile_first_pid) {
+    if (static_cast<int64_t>(em.size()) > tile_capacity)
+      return fail(FLMR_ERR_INVALID_ARG, "tile_capacity %lld < %zu tiles", (long long)tile_capacity, em.size());
+    std::copy(em.begin(), em.end(), tile_end_mask);
+    std::copy(fp.begin(), fp.end(), tile_first_pid);
+  }
   return FLMR_OK;
 }
 

@@ -66,6 +66,9 @@ struct ScanParams {
   int32_t k;                       // 0 = disabled
   uint64_t* cand_keys;             // [n_ctas][nq_pass][k]  (ordered score << 32 | ~local pid)
   // diagnostics
+  int32_t debug_mode;              // 0 = product.  Timing-only experiments (results are garbage):
+                                   // 1 = epilogue releases accumulators unread, 2 = TMEM reads but no
+                                   // max/flush, 3 = mode 1 + MMA issue skipped (pure TMA streaming)
   int* status;
   uint64_t timeout_ns;
 };
@@ -133,10 +136,17 @@ __device__ __forceinline__ void process_chunk(const uint32_t (&v)[32], uint32_t 
 template <int TILE_N>
 __device__ __forceinline__ void epilogue_accumulator(uint32_t taddr, uint64_t mask, float& m,
                                                      float init, float* partial_rb, int lane,
-                                                     uint32_t t_empty_bar) {
+                                                     uint32_t t_empty_bar, int debug_mode) {
   constexpr int kChunks = ScanCfg<TILE_N>::kChunks;
   uint32_t va[32], vb[32];
   int slot = 0;
+  if (debug_mode == 1 || debug_mode == 3) {  // timing experiment: hand the accumulator back unread
+    tc_fence_before_sync();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(t_empty_bar);
+    return;
+  }
+  if (debug_mode == 2) mask = 0ull;          // timing experiment: no passage ends -> no flushes
   FLMR_TMEM_LD32(va, taddr);
 #pragma unroll
   for (int c = 0; c < kChunks; c += 2) {
@@ -297,6 +307,7 @@ flmr_scan_kernel(const __grid_constant__ CUtensorMap tmap_q,
           tc_fence_after_sync();
           const uint32_t q_addr = smem_base + Cfg::kOffQ + mt * kQTileBytes;
           const uint32_t d_tmem = tmem_base + as * TILE_N;
+          if (p.debug_mode != 3) {
 #pragma unroll
           for (int k = 0; k < kDim / 16; ++k) {
             const uint64_t a_desc =
@@ -304,6 +315,7 @@ flmr_scan_kernel(const __grid_constant__ CUtensorMap tmap_q,
             const uint64_t b_desc =
                 make_kmajor_sw128_desc(d_addr + (k >> 2) * Cfg::kDKBlockBytes + (k & 3) * 32);
             tc_mma_ss(d_tmem, a_desc, b_desc, idesc, k > 0 ? 1u : 0u);
+          }
           }
           tc_commit(bar_t_full(as));  // accumulator complete -> epilogue
         }
@@ -352,7 +364,7 @@ flmr_scan_kernel(const __grid_constant__ CUtensorMap tmap_q,
           float* partial_rb = partial + (buf * kRbMax + rb) * Cfg::kSlots;
           const uint32_t taddr = tmem_base + as * TILE_N + (static_cast<uint32_t>(quad * 32) << 16);
           epilogue_accumulator<TILE_N>(taddr, mask, mcar[mt], init, partial_rb, lane,
-                                       bar_t_empty(as));
+                                       bar_t_empty(as), p.debug_mode);
           ++acc;
         }
       }

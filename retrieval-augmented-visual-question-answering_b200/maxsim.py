@@ -18,7 +18,10 @@ def _prep_queries(corpus: FlatCorpus, Q: torch.Tensor) -> torch.Tensor:
         Q = Q.unsqueeze(0)
     if Q.dim() != 3 or Q.size(-1) != _cabi.DIM:
         raise ValueError("Q must be [n_queries, nq, %d], got %s" % (_cabi.DIM, tuple(Q.shape)))
-    return Q.detach().to(device=corpus.device, dtype=torch.bfloat16).contiguous()
+    Q = Q.detach()
+    if not Q.is_cuda or Q.device != corpus.device:
+        Q = Q.to(corpus.device, non_blocking=True)   # H2D of the caller's dtype, cast on the device
+    return Q.to(torch.bfloat16).contiguous()
 
 
 def _stream(corpus: FlatCorpus) -> C.c_void_p:

@@ -1,0 +1,104 @@
+"""CPU: the C-ABI library builds, loads and exports every symbol include/flmr_maxsim.h declares;
+argument validation that happens before any CUDA call; host-side partition logic."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from helpers import ROOT
+from ravqa_b200 import _cabi
+
+
+def header_functions():
+    text = open(os.path.join(ROOT, "include", "flmr_maxsim.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(flmr_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    L = _cabi.lib()
+    names = header_functions()
+    assert len(names) >= 15
+    for n in names:
+        assert hasattr(L, n), "missing export " + n
+    assert set(names) == set(_cabi.SYMBOLS)
+    assert L.flmr_abi_version() == 1
+
+
+def test_library_is_sm100a_tcgen05_build():
+    import subprocess
+    from ravqa_b200 import build
+    sass = subprocess.run(["cuobjdump", "-sass", build.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in sass
+    for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM"):
+        assert mnemonic in sass, mnemonic + " missing: the hot kernel is not tcgen05/TMA code"
+
+
+def test_argument_validation_without_gpu():
+    L = _cabi.lib()
+    h = C.c_void_p()
+    dl = np.array([4, 4], dtype=np.int32)
+    tok = np.zeros((8, 128), dtype=np.uint16)
+    # wrong dim
+    rc = L.flmr_corpus_create(tok.ctypes.data, dl.ctypes.data, 2, 64, 0, 0, 0, C.byref(h))
+    assert rc == 3 and b"dim" in L.flmr_last_error()
+    # zero-length passage is rejected
+    dl0 = np.array([4, 0], dtype=np.int32)
+    rc = L.flmr_corpus_create(tok.ctypes.data, dl0.ctypes.data, 2, 128, 0, 0, 0, C.byref(h))
+    assert rc == 1 and b"zero-length" in L.flmr_last_error()
+    # null pointers
+    assert L.flmr_corpus_create(None, dl.ctypes.data, 2, 128, 0, 0, 0, C.byref(h)) == 1
+    assert L.flmr_topk_merge(None, None, 1, 1, 1, 1, None, None, 0, None) == 1
+    assert L.flmr_maxsim_topk(None, None, None, 1, 32, 5, 0, None, None, None) == 1
+    assert L.flmr_corpus_destroy(None) == 0 and L.flmr_workspace_destroy(None) == 0
+    with pytest.raises(_cabi.FlmrError):
+        _cabi.check(1)
+
+
+def _partition(doclens, n_ctas):
+    L = _cabi.lib()
+    dl = np.ascontiguousarray(doclens, dtype=np.int32)
+    nc = min(n_ctas, len(dl))
+    rb = np.zeros(nc + 1, np.int32)
+    tb = np.zeros(nc + 1, np.int64)
+    nt = C.c_int64()
+    _cabi.check(L.flmr_debug_build_partition(dl.ctypes.data, len(dl), n_ctas, rb.ctypes.data, tb.ctypes.data,
+                                             None, None, 0, C.byref(nt)))
+    em = np.zeros(nt.value, np.uint64)
+    fp = np.zeros(nt.value, np.int32)
+    _cabi.check(L.flmr_debug_build_partition(dl.ctypes.data, len(dl), n_ctas, rb.ctypes.data, tb.ctypes.data,
+                                             em.ctypes.data, fp.ctypes.data, nt.value, C.byref(nt)))
+    return rb, tb, em, fp
+
+
+@pytest.mark.parametrize("seed,n,lo,hi,ctas", [(0, 1000, 1, 64, 148), (1, 37, 100, 700, 148),
+                                                (2, 5000, 1, 4, 16), (3, 3, 180, 180, 148),
+                                                (4, 1, 5, 5, 148), (5, 20000, 180, 180, 148)])
+def test_partition_invariants(seed, n, lo, hi, ctas):
+    rng = np.random.default_rng(seed)
+    dl = rng.integers(lo, hi + 1, size=n)
+    rb, tb, em, fp = _partition(dl, ctas)
+    plen = (dl + 3) // 4 * 4
+    poff = np.concatenate([[0], np.cumsum(plen)])
+    nc = len(rb) - 1
+    assert rb[0] == 0 and rb[-1] == poff[-1] and np.all(np.diff(rb) >= 0)
+    assert set(rb.tolist()) <= set(poff.tolist()), "CTA ranges must start on passage boundaries"
+    # every passage end appears exactly once, at the right tile/bit, in order
+    ends = []
+    for c in range(nc):
+        for t in range(tb[c], tb[c + 1]):
+            bits = int(em[t])
+            slot = 0
+            for g in range(32):
+                if bits >> g & 1:
+                    row_end = rb[c] + (t - tb[c]) * 128 + 4 * g + 4   # exclusive end row
+                    ends.append((int(fp[t]) + slot, row_end))
+                    slot += 1
+            assert bits >> 32 == 0
+    assert [e[0] for e in ends] == list(range(n))
+    assert [e[1] for e in ends] == poff[1:].tolist()
+    # token balance: no CTA holds more than the ideal share + one passage
+    share = poff[-1] / nc
+    assert np.all(np.diff(rb) <= share + plen.max() + 1)
