@@ -90,7 +90,8 @@ struct ScanCfg {
   static constexpr int kKeysBytes = kNqMax * kMaxK * 8;
   static constexpr int kOffMinKey = kOffKeys + kKeysBytes;
   static constexpr int kOffMinPos = kOffMinKey + kNqMax * 8;
-  static constexpr int kOffBars = kOffMinPos + kNqMax * 4 + ((kNqMax * 4) % 8);
+  static constexpr int kOffCarry = kOffMinPos + kNqMax * 4;          // float[kMtMax * 128]
+  static constexpr int kOffBars = (kOffCarry + kMtMax * kTileM * 4 + 7) / 8 * 8;
   static constexpr int kNumBars = 1 + 2 * kDStages + 2 * kAccStages;
   static constexpr int kOffTmemPtr = kOffBars + kNumBars * 8;
   static constexpr int kSmemBytes = kOffTmemPtr + 16 + 1024;  // + slack for 1024-B alignment
@@ -107,30 +108,44 @@ __device__ __forceinline__ float warp_sum(float s) {
   return s;
 }
 
-// 32 accumulator columns (8 groups of 4 tokens).  `bits` bit g: a passage ends after group g.
+// 32 accumulator columns = 8 groups of 4 tokens.  `bits` bit g: a passage ends with group g.
+// Compact on purpose (the epilogue runs one warp per SM sub-partition, so instruction-cache misses
+// and branches are paid in full): 16 FMNMX for the 8 group maxima, then either a 3-instruction
+// fold into the running max, or -- per passage END in this chunk -- one pass of predicated folds
+// + a warp sum.
 __device__ __forceinline__ void process_chunk(const uint32_t (&v)[32], uint32_t bits, float& m,
                                               float init, float* partial_rb, int& slot, int lane) {
-  if (bits == 0u) {
+  float gv[8];
 #pragma unroll
-    for (int g = 0; g < 8; ++g) {
-      const float a = fmax3(__uint_as_float(v[4 * g]), __uint_as_float(v[4 * g + 1]),
-                            __uint_as_float(v[4 * g + 2]));
-      m = fmax3(m, a, __uint_as_float(v[4 * g + 3]));
-    }
-  } else {
-#pragma unroll
-    for (int g = 0; g < 8; ++g) {
-      const float a = fmax3(__uint_as_float(v[4 * g]), __uint_as_float(v[4 * g + 1]),
-                            __uint_as_float(v[4 * g + 2]));
-      m = fmax3(m, a, __uint_as_float(v[4 * g + 3]));
-      if (bits & (1u << g)) {          // warp-uniform: passage boundary
-        const float s = warp_sum(m);
-        if (lane == 0) partial_rb[slot] = s;
-        ++slot;
-        m = init;
-      }
-    }
+  for (int g = 0; g < 8; ++g) {
+    const float a = fmax3(__uint_as_float(v[4 * g]), __uint_as_float(v[4 * g + 1]),
+                          __uint_as_float(v[4 * g + 2]));
+    gv[g] = fmaxf(a, __uint_as_float(v[4 * g + 3]));
   }
+  if (bits == 0u) {
+    const float x = fmax3(gv[0], gv[1], gv[2]);
+    const float y = fmax3(gv[3], gv[4], gv[5]);
+    m = fmax3(m, x, y);
+    m = fmax3(m, gv[6], gv[7]);
+    return;
+  }
+  uint32_t live = 0xFFu;  // groups not yet consumed by a finished passage
+#pragma unroll 1
+  while (bits) {          // warp-uniform: one iteration per passage ending in this chunk
+    const uint32_t upto = bits ^ (bits - 1u);  // groups 0..(lowest set bit)
+    const uint32_t seg = upto & live;
+    float s = m;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) s = fmaxf(s, ((seg >> g) & 1u) ? gv[g] : -INFINITY);
+    s = warp_sum(s);
+    if (lane == 0) partial_rb[slot] = s;
+    ++slot;
+    m = init;
+    live &= ~upto;
+    bits &= bits - 1u;
+  }
+#pragma unroll
+  for (int g = 0; g < 8; ++g) m = fmaxf(m, ((live >> g) & 1u) ? gv[g] : -INFINITY);
 }
 
 template <int TILE_N>
@@ -148,7 +163,7 @@ __device__ __forceinline__ void epilogue_accumulator(uint32_t taddr, uint64_t ma
   }
   if (debug_mode == 2) mask = 0ull;          // timing experiment: no passage ends -> no flushes
   FLMR_TMEM_LD32(va, taddr);
-#pragma unroll
+#pragma unroll 1
   for (int c = 0; c < kChunks; c += 2) {
     FLMR_TMEM_WAIT_LD32(va);
     FLMR_TMEM_LD32(vb, taddr + (c + 1) * 32);
@@ -175,8 +190,8 @@ __device__ __forceinline__ uint64_t shfl64(uint64_t v, int src) {
 }
 
 // Replace the current minimum of an unsorted k-entry list by `cand`, then recompute the minimum.
-__device__ __forceinline__ void topk_replace_min(uint64_t* keys, int k, uint64_t cand,
-                                                 uint64_t& minkey, int& minpos, int lane) {
+__device__ __noinline__ void topk_replace_min(uint64_t* keys, int k, uint64_t cand,
+                                              uint64_t& minkey, int& minpos, int lane) {
   if (lane == 0) keys[minpos] = cand;
   __syncwarp();
   uint64_t mk = ~0ull;
@@ -334,9 +349,10 @@ flmr_scan_kernel(const __grid_constant__ CUtensorMap tmap_q,
     const float init = p.init_val;
     const int rows_valid_rb = p.nq_pass * p.rbq;  // row blocks that belong to a query
 
-    float mcar[kMtMax];
+    // running max of the passage that straddles consecutive D tiles, per (query tile, row)
+    float* carry = reinterpret_cast<float*>(smem + Cfg::kOffCarry) + (threadIdx.x - 64);
 #pragma unroll
-    for (int i = 0; i < kMtMax; ++i) mcar[i] = init;
+    for (int i = 0; i < kMtMax; ++i) carry[i * kTileM] = init;
 
     uint32_t acc = 0;
     uint64_t mask_next = 0;
@@ -353,9 +369,10 @@ flmr_scan_kernel(const __grid_constant__ CUtensorMap tmap_q,
         fpid_next = __ldg(p.tile_first_pid + tile_base + t + 1);
       }
       const int buf = t & 1;
-#pragma unroll
-      for (int mt = 0; mt < kMtMax; ++mt) {
-        if (mt < p.n_mtiles) {
+#pragma unroll 1
+      for (int mt = 0; mt < p.n_mtiles; ++mt) {
+        {
+          float m = carry[mt * kTileM];
           const uint32_t as = acc % Cfg::kAccStages;
           const uint32_t aph = (acc / Cfg::kAccStages) & 1;
           mbar_wait(bar_t_full(as), aph, p.status, kDevTimeoutEpilogue, p.timeout_ns);
@@ -363,8 +380,9 @@ flmr_scan_kernel(const __grid_constant__ CUtensorMap tmap_q,
           const int rb = mt * 4 + quad;
           float* partial_rb = partial + (buf * kRbMax + rb) * Cfg::kSlots;
           const uint32_t taddr = tmem_base + as * TILE_N + (static_cast<uint32_t>(quad * 32) << 16);
-          epilogue_accumulator<TILE_N>(taddr, mask, mcar[mt], init, partial_rb, lane,
-                                       bar_t_empty(as), p.debug_mode);
+          epilogue_accumulator<TILE_N>(taddr, mask, m, init, partial_rb, lane, bar_t_empty(as),
+                                       p.debug_mode);
+          carry[mt * kTileM] = m;
           ++acc;
         }
       }
@@ -373,10 +391,12 @@ flmr_scan_kernel(const __grid_constant__ CUtensorMap tmap_q,
 
       // ---- finalize: per (query, passage ending in this tile) ----
       const int n_slots = __popcll(mask);
+#pragma unroll 1
       for (int b = ew; b < p.nq_pass; b += 4) {
         uint64_t minkey = minkey_s[b];
         int minpos = minpos_s[b];
         bool dirty = false;
+#pragma unroll 1
         for (int s0 = 0; s0 < n_slots; s0 += 32) {
           const int slot = s0 + lane;
           const bool valid = slot < n_slots;
@@ -384,6 +404,7 @@ flmr_scan_kernel(const __grid_constant__ CUtensorMap tmap_q,
           uint64_t key = 0ull;
           if (valid) {
             const float* pr = partial + (buf * kRbMax + b * p.rbq) * Cfg::kSlots + slot;
+#pragma unroll 2
             for (int r = 0; r < p.rbq; ++r) sc += pr[r * Cfg::kSlots];
             const int64_t pid = static_cast<int64_t>(first_pid) + slot;
             const int64_t gi = static_cast<int64_t>(b) * p.n_passages + pid;

@@ -37,6 +37,8 @@ def maxsim_scores(corpus: FlatCorpus, Q: torch.Tensor, relu: bool = False,
         out = torch.empty((B, corpus.n_passages), dtype=torch.float32, device=corpus.device)
     elif out.shape != (B, corpus.n_passages) or out.dtype != torch.float32 or not out.is_contiguous():
         raise ValueError("out must be a contiguous fp32 [n_queries, n_passages] CUDA tensor")
+    if B == 0:
+        return out
     with torch.cuda.device(corpus.device):
         _cabi.check(_cabi.lib().flmr_maxsim_scores(
             corpus.handle, corpus.workspace(), C.c_void_p(Qd.data_ptr()), B, nq,
@@ -53,6 +55,8 @@ def maxsim_topk(corpus: FlatCorpus, Q: torch.Tensor, k: int, relu: bool = False
     B, nq = Qd.size(0), Qd.size(1)
     scores = torch.empty((B, k), dtype=torch.float32, device=corpus.device)
     pids = torch.empty((B, k), dtype=torch.int64, device=corpus.device)
+    if B == 0:
+        return scores, pids
     with torch.cuda.device(corpus.device):
         _cabi.check(_cabi.lib().flmr_maxsim_topk(
             corpus.handle, corpus.workspace(), C.c_void_p(Qd.data_ptr()), B, nq, k,
