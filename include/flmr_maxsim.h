@@ -70,6 +70,7 @@ extern "C" {
 #define FLMR_DIM 128        /* embedding dim of FLMR / ColBERT (CB/infra/config/settings.py:101) */
 #define FLMR_TOKEN_GROUP 4  /* passages are stored padded to a multiple of this many tokens     */
 #define FLMR_MAX_K 128      /* largest k of the fused top-k                                     */
+#define FLMR_TILE_TOKENS 96 /* passage tokens per streamed tile of the scan kernel              */
 
 typedef struct flmr_corpus flmr_corpus_t;       /* resident passage-token shard            */
 typedef struct flmr_workspace flmr_workspace_t; /* per-caller scratch (candidates, Q pad)  */
@@ -150,12 +151,13 @@ int flmr_debug_maxsim_scores_simt(const flmr_corpus_t* corpus, const void* d_q, 
                                   int nq, unsigned flags, float* d_out_scores, void* stream);
 
 /* Test infrastructure, host-only (no GPU needed): the token-balanced CTA partition + per-tile
- * passage-end metadata the scan kernel consumes, for `n_ctas` persistent CTAs and 128-token tiles.
+ * passage-end metadata the scan kernel consumes, for `n_ctas` persistent CTAs and
+ * FLMR_TILE_TOKENS-token tiles (bit g of a tile's mask: a passage ends with 4-token group g).
  * cta_row_begin / cta_tile_base hold min(n_ctas, n_passages) + 1 entries; tile arrays may be NULL
  * to query *n_tiles_out only. */
 int flmr_debug_build_partition(const int32_t* h_doclens, int64_t n_passages, int n_ctas,
                                int32_t* cta_row_begin, int64_t* cta_tile_base,
-                               uint64_t* tile_end_mask, int32_t* tile_first_pid,
+                               uint32_t* tile_end_mask, int32_t* tile_first_pid,
                                int64_t tile_capacity, int64_t* n_tiles_out);
 
 /* Kernels launched by this library on the calling thread since the last reset (bench evidence). */

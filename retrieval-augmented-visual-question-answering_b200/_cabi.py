@@ -18,6 +18,7 @@ CORPUS_ADOPT = 1
 DIM = 128
 TOKEN_GROUP = 4
 MAX_K = 128
+TILE_TOKENS = 96
 
 # every symbol include/flmr_maxsim.h declares (tests check the .so exports all of them)
 SYMBOLS = [

@@ -137,6 +137,18 @@ __device__ __forceinline__ void tc_mma_ss(uint32_t d_tmem, uint64_t a_desc, uint
       : "memory");
 }
 
+// D[tmem] (+)= A[tmem] * B[smem]^T: the A operand (128 rows x 16 bf16 per MMA = 8 TMEM columns,
+// row = lane, two consecutive K elements per 32-bit column) is read from tensor memory.
+__device__ __forceinline__ void tc_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc,
+                                          uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
 // Shared-memory matrix descriptor, K-major operand, 128-byte swizzle, rows of 128 B
 // (64 bf16), 8-row groups 1024 B apart.  Field layout: start>>4 [0,14) | LBO>>4 [16,30) |
 // SBO>>4 [32,46) | version=1 [46,48) | layout type [61,64) (2 = SWIZZLE_128B).
@@ -182,6 +194,23 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16_f32(int m, int n) {
                  "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]),     \
                  "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]),     \
                  "+r"(v[30]), "+r"(v[31])::"memory")
+
+// 32 registers per thread -> 32 lanes x 32 consecutive 32-bit TMEM columns.
+#define FLMR_TMEM_ST32(taddr, v)                                                                   \
+  asm volatile(                                                                                    \
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "                                              \
+      "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,"                                   \
+      "%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"                          \
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]),   \
+      "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]),             \
+      "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]),          \
+      "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]),          \
+      "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])                                               \
+      : "memory")
+
+__device__ __forceinline__ void tmem_wait_st() {
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
 
 __device__ __forceinline__ float fmax3(float a, float b, float c) {
   float r;

@@ -29,8 +29,6 @@ namespace {
 
 using namespace flmr;
 
-constexpr int kTileN = 128;  // passage tokens per streamed tile
-
 static_assert(kMaxK == FLMR_MAX_K, "header / kernel top-k capacity mismatch");
 static_assert(kGroup == FLMR_TOKEN_GROUP, "header / kernel token group mismatch");
 static_assert(kDim == FLMR_DIM, "header / kernel dim mismatch");
@@ -299,7 +297,7 @@ struct flmr_corpus {
   int32_t* d_doclen = nullptr;         // [n_passages] real lengths
   int32_t* d_cta_row_begin = nullptr;  // [n_ctas + 1]
   int64_t* d_cta_tile_base = nullptr;  // [n_ctas + 1]
-  uint64_t* d_tile_end_mask = nullptr; // [n_tiles]
+  uint32_t* d_tile_end_mask = nullptr; // [n_tiles]
   int32_t* d_tile_first_pid = nullptr; // [n_tiles]
   CUtensorMap tmap_d;
 };
@@ -308,12 +306,11 @@ struct flmr_workspace {
   const flmr_corpus* corpus = nullptr;
   int device = 0;
   int max_queries = 0, max_nq = 0;
-  __nv_bfloat16* d_qpad = nullptr;     // [kMtMax*128, 128]
+  __nv_bfloat16* d_qpad = nullptr;     // [kMtMax*128, 128] staged (zero-padded) queries of one pass
   uint64_t* d_cand_keys = nullptr;     // [n_ctas][kNqMax][kMaxK]
   float* d_acc = nullptr;              // [n_passages] lazily allocated (row-sliced queries)
   int* h_status = nullptr;             // pinned + mapped: readable by the host even after a device trap
   int* d_status = nullptr;             // device alias of h_status
-  CUtensorMap tmap_q;
 };
 
 namespace {
@@ -336,7 +333,7 @@ int dev_upload(T** dptr, const std::vector<T>& h, int64_t* bytes_acc) {
 // Token-balanced split of the passages into n_ctas contiguous ranges + per-tile metadata.
 void build_partition(const std::vector<int64_t>& poff, int n_ctas, int tile_n,
                      std::vector<int32_t>* cta_row_begin, std::vector<int64_t>* cta_tile_base,
-                     std::vector<uint64_t>* tile_end_mask, std::vector<int32_t>* tile_first_pid) {
+                     std::vector<uint32_t>* tile_end_mask, std::vector<int32_t>* tile_first_pid) {
   const int64_t n = static_cast<int64_t>(poff.size()) - 1;
   const int64_t rows = poff[n];
   std::vector<int64_t> pbeg(n_ctas + 1);
@@ -356,7 +353,7 @@ void build_partition(const std::vector<int64_t>& poff, int n_ctas, int tile_n,
     (*cta_tile_base)[c] = tiles;
     if (c < n_ctas) tiles += (poff[pbeg[c + 1]] - poff[pbeg[c]] + tile_n - 1) / tile_n;
   }
-  tile_end_mask->assign(tiles, 0ull);
+  tile_end_mask->assign(tiles, 0u);
   tile_first_pid->assign(tiles, 0);
   for (int c = 0; c < n_ctas; ++c) {
     const int64_t r0 = poff[pbeg[c]];
@@ -367,7 +364,7 @@ void build_partition(const std::vector<int64_t>& poff, int n_ctas, int tile_n,
       const int64_t last = poff[p + 1] - 1 - r0;  // last stored row of p, relative to the CTA
       const int64_t t = last / tile_n;
       const int g = static_cast<int>((last % tile_n) / kGroup);
-      (*tile_end_mask)[tb + t] |= (1ull << g);
+      (*tile_end_mask)[tb + t] |= (1u << g);
       if (!seen[t]) {
         seen[t] = 1;
         (*tile_first_pid)[tb + t] = static_cast<int32_t>(p);
@@ -378,10 +375,10 @@ void build_partition(const std::vector<int64_t>& poff, int n_ctas, int tile_n,
 
 int launch_scan(const flmr_corpus* c, flmr_workspace* ws, const ScanParams& p, cudaStream_t st) {
   static bool attr_set[64] = {};
-  auto kern = flmr_scan_kernel<kTileN>;
+  auto kern = flmr_scan_kernel;
   if (c->device < 64 && !attr_set[c->device]) {
     FLMR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   ScanCfg<kTileN>::kSmemBytes));
+                                   ScanSmem::kBytes));
     attr_set[c->device] = true;
   }
   EventPair ev{};
@@ -390,7 +387,8 @@ int launch_scan(const flmr_corpus* c, flmr_workspace* ws, const ScanParams& p, c
     FLMR_CUDA(cudaEventCreate(&ev.b));
     FLMR_CUDA(cudaEventRecord(ev.a, st));
   }
-  kern<<<c->n_ctas, kScanThreads, ScanCfg<kTileN>::kSmemBytes, st>>>(ws->tmap_q, c->tmap_d, p);
+  (void)ws;
+  kern<<<c->n_ctas, kScanThreads, ScanSmem::kBytes, st>>>(c->tmap_d, p);
   FLMR_CUDA(cudaGetLastError());
   ++g_launches;
   if (g_profiling) {
@@ -447,6 +445,7 @@ int run_search(const flmr_corpus* c, flmr_workspace* ws, const void* d_q, int n_
   p.init_val = (flags & FLMR_FLAG_RELU) ? 0.f : -INFINITY;
   p.n_passages = c->n_passages;
   p.cand_keys = ws->d_cand_keys;
+  p.q_pad = reinterpret_cast<const uint4*>(ws->d_qpad);
   p.status = ws->d_status;
   p.timeout_ns = 4000000000ull;
   if (const char* e = getenv("FLMR_DEBUG_MODE")) p.debug_mode = atoi(e);
@@ -648,7 +647,7 @@ int flmr_corpus_create(const void* tokens, const int32_t* h_doclens, int64_t n_p
   {
     std::vector<int32_t> row_begin, first_pid;
     std::vector<int64_t> tile_base;
-    std::vector<uint64_t> end_mask;
+    std::vector<uint32_t> end_mask;
     build_partition(poff, n_ctas, kTileN, &row_begin, &tile_base, &end_mask, &first_pid);
     c->n_tiles = static_cast<int64_t>(end_mask.size());
     if ((rc = dev_upload(&c->d_cta_row_begin, row_begin, &c->hbm_bytes))) return bail(rc);
@@ -717,8 +716,6 @@ int flmr_workspace_create(const flmr_corpus_t* c, int max_queries, int max_nq,
       (e = cudaHostGetDevicePointer(reinterpret_cast<void**>(&ws->d_status), ws->h_status, 0)) != cudaSuccess)
     return bail(fail(FLMR_ERR_CUDA, "workspace allocation failed: %s", cudaGetErrorString(e)));
   *ws->h_status = 0;
-  int rc = encode_rows_map(&ws->tmap_q, ws->d_qpad, static_cast<uint64_t>(kMtMax) * kTileM, kTileM);
-  if (rc) return bail(rc);
   *out = ws;
   return FLMR_OK;
 }
@@ -797,7 +794,7 @@ int flmr_debug_maxsim_scores_simt(const flmr_corpus_t* c, const void* d_q, int n
 
 int flmr_debug_build_partition(const int32_t* h_doclens, int64_t n_passages, int n_ctas,
                                int32_t* cta_row_begin, int64_t* cta_tile_base,
-                               uint64_t* tile_end_mask, int32_t* tile_first_pid,
+                               uint32_t* tile_end_mask, int32_t* tile_first_pid,
                                int64_t tile_capacity, int64_t* n_tiles_out) {
   if (!h_doclens || n_passages <= 0 || n_ctas < 1 || !cta_row_begin || !cta_tile_base || !n_tiles_out)
     return fail(FLMR_ERR_INVALID_ARG, "bad argument");
@@ -810,7 +807,7 @@ int flmr_debug_build_partition(const int32_t* h_doclens, int64_t n_passages, int
   n_ctas = static_cast<int>(std::min<int64_t>(n_ctas, n_passages));
   std::vector<int32_t> rb, fp;
   std::vector<int64_t> tb;
-  std::vector<uint64_t> em;
+  std::vector<uint32_t> em;
   build_partition(poff, n_ctas, kTileN, &rb, &tb, &em, &fp);
   *n_tiles_out = static_cast<int64_t>(em.size());
   std::copy(rb.begin(), rb.end(), cta_row_begin);

@@ -66,7 +66,7 @@ def _partition(doclens, n_ctas):
     nt = C.c_int64()
     _cabi.check(L.flmr_debug_build_partition(dl.ctypes.data, len(dl), n_ctas, rb.ctypes.data, tb.ctypes.data,
                                              None, None, 0, C.byref(nt)))
-    em = np.zeros(nt.value, np.uint64)
+    em = np.zeros(nt.value, np.uint32)
     fp = np.zeros(nt.value, np.int32)
     _cabi.check(L.flmr_debug_build_partition(dl.ctypes.data, len(dl), n_ctas, rb.ctypes.data, tb.ctypes.data,
                                              em.ctypes.data, fp.ctypes.data, nt.value, C.byref(nt)))
@@ -91,12 +91,12 @@ def test_partition_invariants(seed, n, lo, hi, ctas):
         for t in range(tb[c], tb[c + 1]):
             bits = int(em[t])
             slot = 0
-            for g in range(32):
+            for g in range(_cabi.TILE_TOKENS // 4):
                 if bits >> g & 1:
-                    row_end = rb[c] + (t - tb[c]) * 128 + 4 * g + 4   # exclusive end row
+                    row_end = rb[c] + (t - tb[c]) * _cabi.TILE_TOKENS + 4 * g + 4   # exclusive end row
                     ends.append((int(fp[t]) + slot, row_end))
                     slot += 1
-            assert bits >> 32 == 0
+            assert bits >> (_cabi.TILE_TOKENS // 4) == 0
     assert [e[0] for e in ends] == list(range(n))
     assert [e[1] for e in ends] == poff[1:].tolist()
     # token balance: no CTA holds more than the ideal share + one passage
