@@ -267,56 +267,62 @@ flmr_scan_kernel(const __grid_constant__ CUtensorMap tmap_d, const ScanParams p)
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
-      for (int t = 0; t < n_tiles; ++t) {
-        const int s = t % kDStages;
-        const uint32_t ph = (t / kDStages) & 1;
-        mbar_wait(bar_d_empty(s), ph ^ 1u, p.status, kDevTimeoutProducer, p.timeout_ns);
+    // The whole warp runs the loop (warp-uniform control flow keeps addresses in uniform
+    // registers); one elected lane issues the bulk copies.
+    for (int t = 0; t < n_tiles; ++t) {
+      const int s = t % kDStages;
+      const uint32_t ph = (t / kDStages) & 1;
+      mbar_wait(bar_d_empty(s), ph ^ 1u, p.status, kDevTimeoutProducer, p.timeout_ns);
+      if (elect_one_sync()) {
         mbar_arrive_expect_tx(bar_d_full(s), kDTileBytes);
         const uint32_t dst = smem_base + S::kOffD + s * kDTileBytes;
         const int32_t row = row_begin + t * kTileN;
         tma_load_2d(dst, &tmap_d, bar_d_full(s), 0, row, kPolicyEvictFirst);
         tma_load_2d(dst + kDKBlockBytes, &tmap_d, bar_d_full(s), 64, row, kPolicyEvictFirst);
       }
+      __syncwarp();
     }
-    __syncwarp();
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16_f32(kTileM, kTileN);
-      mbar_wait(bar_q_full, 0, p.status, kDevTimeoutMma, p.timeout_ns);  // queries are in TMEM
+    // Warp-uniform loop; one elected lane (always the same one) issues tcgen05.mma / commit, so the
+    // descriptors stay in uniform registers instead of a per-instruction broadcast waterfall.
+    constexpr uint32_t idesc = make_idesc_bf16_f32(kTileM, kTileN);
+    mbar_wait(bar_q_full, 0, p.status, kDevTimeoutMma, p.timeout_ns);  // queries are in TMEM
+    tc_fence_after_sync();
+    uint32_t as = 0, aph = 0;  // accumulator stage / phase, advanced per accumulator
+    for (int t = 0; t < n_tiles; ++t) {
+      const int s = t % kDStages;
+      const uint32_t ph = (t / kDStages) & 1;
+      mbar_wait(bar_d_full(s), ph, p.status, kDevTimeoutMma, p.timeout_ns);
       tc_fence_after_sync();
-      uint32_t as = 0, aph = 0;  // accumulator stage / phase, advanced per accumulator
-      for (int t = 0; t < n_tiles; ++t) {
-        const int s = t % kDStages;
-        const uint32_t ph = (t / kDStages) & 1;
-        mbar_wait(bar_d_full(s), ph, p.status, kDevTimeoutMma, p.timeout_ns);
-        tc_fence_after_sync();
-        const uint32_t d_addr = smem_base + S::kOffD + s * kDTileBytes;
+      const uint64_t b_desc0 = make_kmajor_sw128_desc(smem_base + S::kOffD + s * kDTileBytes);
 #pragma unroll 1
-        for (int mt = 0; mt < n_mtiles; ++mt) {
-          mbar_wait(bar_t_empty(as), aph ^ 1u, p.status, kDevTimeoutMma, p.timeout_ns);
-          tc_fence_after_sync();
-          const uint32_t d_tmem = tmem_base + acc_col0 + as * kTileN;
-          const uint32_t a_tmem = tmem_base + mt * kQCols;
+      for (int mt = 0; mt < n_mtiles; ++mt) {
+        mbar_wait(bar_t_empty(as), aph ^ 1u, p.status, kDevTimeoutMma, p.timeout_ns);
+        tc_fence_after_sync();
+        const uint32_t d_tmem = tmem_base + acc_col0 + as * kTileN;
+        const uint32_t a_tmem = tmem_base + mt * kQCols;
+        if (elect_one_sync()) {
           if (p.debug_mode != 3) {
 #pragma unroll
             for (int k = 0; k < kDim / 16; ++k) {
+              // advance the start-address field (16-byte units) inside the descriptor
               const uint64_t b_desc =
-                  make_kmajor_sw128_desc(d_addr + (k >> 2) * kDKBlockBytes + (k & 3) * 32);
+                  b_desc0 + static_cast<uint64_t>(((k >> 2) * kDKBlockBytes + (k & 3) * 32) >> 4);
               tc_mma_ts(d_tmem, a_tmem + k * 8, b_desc, idesc, k > 0 ? 1u : 0u);
             }
           }
           tc_commit(bar_t_full(as));  // accumulator complete -> epilogue
-          if (++as == acc_stages) {
-            as = 0;
-            aph ^= 1u;
-          }
         }
-        tc_commit(bar_d_empty(s));    // all MMAs reading this D stage complete -> producer
+        __syncwarp();
+        if (++as == acc_stages) {
+          as = 0;
+          aph ^= 1u;
+        }
       }
+      if (elect_one_sync()) tc_commit(bar_d_empty(s));  // MMAs reading this D stage done -> producer
+      __syncwarp();
     }
-    __syncwarp();
   } else {
     // ===================== epilogue =====================
     const int ew = warp - 2;          // epilogue warp 0..7
