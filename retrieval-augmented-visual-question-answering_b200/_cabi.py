@@ -18,7 +18,16 @@ CORPUS_ADOPT = 1
 DIM = 128
 TOKEN_GROUP = 4
 MAX_K = 128
-TILE_TOKENS = 96
+
+
+def _header_define(name: str) -> int:
+    import re
+    hdr = os.path.join(os.path.dirname(os.path.abspath(_build.__file__)), "..", "include", "flmr_maxsim.h")
+    m = re.search(r"#define\s+%s\s+(\d+)" % name, open(hdr).read())
+    return int(m.group(1))
+
+
+TILE_TOKENS = _header_define("FLMR_TILE_TOKENS")
 
 # every symbol include/flmr_maxsim.h declares (tests check the .so exports all of them)
 SYMBOLS = [

@@ -34,13 +34,14 @@
 //   * each query is padded to a multiple of 32 rows with zero rows (contribute exactly 0, like the
 //     reference's masked query tokens), so a warp's 32 TMEM lanes always belong to one query.
 #pragma once
+#include "../../include/flmr_maxsim.h"
 #include "flmr_device.cuh"
 
 namespace flmr {
 
 constexpr int kDim = 128;
 constexpr int kTileM = 128;               // query rows per MMA (UMMA M)
-constexpr int kTileN = 96;                // passage tokens per streamed tile (UMMA N)
+constexpr int kTileN = FLMR_TILE_TOKENS;  // passage tokens per streamed tile (UMMA N)
 constexpr int kMtMax = 5;                 // resident 128-row query tiles per pass (5 x 64 TMEM cols)
 constexpr int kRbMax = kMtMax * 4;        // resident 32-row blocks
 constexpr int kNqMax = kRbMax;            // queries per pass (each has >= 1 row block)
@@ -50,14 +51,15 @@ constexpr int kSlots = kTileN / kGroup;   // passage ends per tile, at most (24 
 constexpr int kChunks = kTileN / 32;      // 32-column chunks per accumulator
 constexpr int kQCols = kDim / 2;          // TMEM columns of one query tile (bf16 pairs)
 constexpr int kMaxAccStages = 4;
-constexpr int kDStages = 7;
+constexpr int kDStages = (kTileN == 96) ? 7 : 10;
 constexpr int kDTileBytes = kTileN * kDim * 2;   // 24 KiB: [2 k-blocks][96 rows][64 bf16]
 constexpr int kDKBlockBytes = kTileN * 128;      // 12 KiB
-constexpr int kEpiWarps = 8;
+constexpr int kEpiWarps = 8;                      // warps 2..9: two warpgroups draining TMEM
 constexpr int kEpiThreads = kEpiWarps * 32;
-constexpr int kScanThreads = 64 + kEpiThreads;
+constexpr int kRedWarps = 2;                      // warps 10..11: score finalisation + top-k
+constexpr int kScanThreads = 64 + kEpiThreads + kRedWarps * 32;
 
-static_assert(kChunks == 3, "epilogue is written for three 32-column chunks");
+static_assert(kTileN == 96 || kTileN == 64, "tile width must be 96 or 64 tokens");
 static_assert(kDKBlockBytes % 1024 == 0, "swizzle atoms need 1024-B aligned k-blocks");
 
 struct ScanParams {
@@ -82,7 +84,9 @@ struct ScanParams {
   // diagnostics
   int32_t debug_mode;              // 0 = product.  Timing-only experiments (results are garbage):
                                    // 1 = epilogue releases accumulators unread, 2 = TMEM reads but no
-                                   // passage ends, 3 = mode 1 + MMA issue skipped (pure TMA streaming)
+                                   // passage ends, 3 = mode 1 + MMA issue skipped (pure TMA streaming),
+                                   // 4 = MMA issue never waits for the epilogue (epilogue idle),
+                                   // 5 = mode 4 without the per-accumulator commit
   int* status;
   uint64_t timeout_ns;
 };
@@ -96,8 +100,9 @@ struct ScanSmem {
   static constexpr int kOffMinKey = kOffKeys + kKeysBytes;           // u64[kNqMax]
   static constexpr int kOffMinPos = kOffMinKey + kNqMax * 8;         // int[kNqMax]
   static constexpr int kOffCarry = kOffMinPos + kNqMax * 4;          // float[kMtMax * 128]
-  static constexpr int kOffBars = (kOffCarry + kMtMax * kTileM * 4 + 7) / 8 * 8;
-  static constexpr int kNumBars = 1 + 2 * kDStages + 2 * kMaxAccStages;
+  static constexpr int kOffCarryVer = kOffCarry + kMtMax * kTileM * 4;   // u32[kMtMax * 4]
+  static constexpr int kOffBars = (kOffCarryVer + kMtMax * 4 * 4 + 7) / 8 * 8;
+  static constexpr int kNumBars = 1 + 2 * kDStages + 2 * kMaxAccStages + 4;
   static constexpr int kOffTmemPtr = kOffBars + kNumBars * 8;
   static constexpr int kBytes = kOffTmemPtr + 16 + 1024;  // + slack for 1024-B alignment
   static_assert(kBytes <= 232448, "exceeds 227 KiB of shared memory per CTA");
@@ -222,6 +227,10 @@ flmr_scan_kernel(const __grid_constant__ CUtensorMap tmap_d, const ScanParams p)
   auto bar_d_empty = [&](int s) { return bar_base + 8u * (1 + kDStages + s); };
   auto bar_t_full = [&](int s) { return bar_base + 8u * (1 + 2 * kDStages + s); };
   auto bar_t_empty = [&](int s) { return bar_base + 8u * (1 + 2 * kDStages + kMaxAccStages + s); };
+  auto bar_p_full = [&](int b) { return bar_base + 8u * (1 + 2 * kDStages + 2 * kMaxAccStages + b); };
+  auto bar_p_empty = [&](int b) {
+    return bar_base + 8u * (1 + 2 * kDStages + 2 * kMaxAccStages + 2 + b);
+  };
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + S::kOffTmemPtr);
 
   const int32_t row_begin = p.cta_row_begin[cta];
@@ -241,7 +250,11 @@ flmr_scan_kernel(const __grid_constant__ CUtensorMap tmap_d, const ScanParams p)
     }
     for (int s = 0; s < kMaxAccStages; ++s) {
       mbar_init(bar_t_full(s), 1);
-      mbar_init(bar_t_empty(s), 4);  // one arrive per warp of the owning epilogue warpgroup
+      mbar_init(bar_t_empty(s), 4);  // one arrive per warp of the draining epilogue warpgroup
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(bar_p_full(b), kEpiWarps);   // partial sums of a D tile complete
+      mbar_init(bar_p_empty(b), kRedWarps);  // ... and consumed by the reducer warps
     }
     mbar_fence_init();
   }
@@ -250,15 +263,17 @@ flmr_scan_kernel(const __grid_constant__ CUtensorMap tmap_d, const ScanParams p)
   }
   if (warp >= 2) {
     const int et = threadIdx.x - 64;
+    constexpr int kInitThreads = kEpiThreads + kRedWarps * 32;
     // top-k lists start empty (key 0 sorts below every real candidate)
     uint64_t* keys = reinterpret_cast<uint64_t*>(smem + S::kOffKeys);
-    for (int i = et; i < kNqMax * kMaxK; i += kEpiThreads) keys[i] = 0ull;
+    for (int i = et; i < kNqMax * kMaxK; i += kInitThreads) keys[i] = 0ull;
     if (et < kNqMax) {
       reinterpret_cast<uint64_t*>(smem + S::kOffMinKey)[et] = 0ull;
       reinterpret_cast<int*>(smem + S::kOffMinPos)[et] = 0;
     }
     float* carry0 = reinterpret_cast<float*>(smem + S::kOffCarry);
-    for (int i = et; i < kMtMax * kTileM; i += kEpiThreads) carry0[i] = p.init_val;
+    for (int i = et; i < kMtMax * kTileM; i += kInitThreads) carry0[i] = p.init_val;
+    if (et < kMtMax * 4) reinterpret_cast<uint32_t*>(smem + S::kOffCarryVer)[et] = 0u;
   }
   tc_fence_before_sync();
   __syncthreads();
@@ -298,8 +313,10 @@ flmr_scan_kernel(const __grid_constant__ CUtensorMap tmap_d, const ScanParams p)
       const uint64_t b_desc0 = make_kmajor_sw128_desc(smem_base + S::kOffD + s * kDTileBytes);
 #pragma unroll 1
       for (int mt = 0; mt < n_mtiles; ++mt) {
-        mbar_wait(bar_t_empty(as), aph ^ 1u, p.status, kDevTimeoutMma, p.timeout_ns);
-        tc_fence_after_sync();
+        if (p.debug_mode < 4) {  // (modes 4/5: timing experiment, never wait for the epilogue)
+          mbar_wait(bar_t_empty(as), aph ^ 1u, p.status, kDevTimeoutMma, p.timeout_ns);
+          tc_fence_after_sync();
+        }
         const uint32_t d_tmem = tmem_base + acc_col0 + as * kTileN;
         const uint32_t a_tmem = tmem_base + mt * kQCols;
         if (elect_one_sync()) {
@@ -312,7 +329,7 @@ flmr_scan_kernel(const __grid_constant__ CUtensorMap tmap_d, const ScanParams p)
               tc_mma_ts(d_tmem, a_tmem + k * 8, b_desc, idesc, k > 0 ? 1u : 0u);
             }
           }
-          tc_commit(bar_t_full(as));  // accumulator complete -> epilogue
+          if (p.debug_mode != 5) tc_commit(bar_t_full(as));  // accumulator complete -> epilogue
         }
         __syncwarp();
         if (++as == acc_stages) {
@@ -323,17 +340,19 @@ flmr_scan_kernel(const __grid_constant__ CUtensorMap tmap_d, const ScanParams p)
       if (elect_one_sync()) tc_commit(bar_d_empty(s));  // MMAs reading this D stage done -> producer
       __syncwarp();
     }
-  } else {
-    // ===================== epilogue =====================
+  } else if (warp < 2 + kEpiWarps) {
+    // ===================== epilogue (TMEM drain) =====================
+    // Accumulators are numbered in MMA issue order, a = t * n_mtiles + mt; warpgroup g drains the
+    // accumulators with (a & 1) == g, so the two warpgroups alternate strictly.  The running max of
+    // the passage straddling D tiles is per (query tile, row): when n_mtiles is odd it changes
+    // hands between the warpgroups every tile, through shared memory + a version flag.
     const int ew = warp - 2;          // epilogue warp 0..7
-    const int wg = ew >> 2;           // warpgroup: owns query tiles with (mt & 1) == wg
+    const int wg = ew >> 2;
     const int quad = warp & 3;        // TMEM lane quadrant this warp may access
     const uint32_t lane_base = static_cast<uint32_t>(quad * 32) << 16;
     float* partial = reinterpret_cast<float*>(smem + S::kOffPartial);
-    uint64_t* keys = reinterpret_cast<uint64_t*>(smem + S::kOffKeys);
-    uint64_t* minkey_s = reinterpret_cast<uint64_t*>(smem + S::kOffMinKey);
-    int* minpos_s = reinterpret_cast<int*>(smem + S::kOffMinPos);
     float* carry = reinterpret_cast<float*>(smem + S::kOffCarry) + quad * 32 + lane;
+    volatile uint32_t* carry_ver = reinterpret_cast<volatile uint32_t*>(smem + S::kOffCarryVer) + quad;
     const float init = p.init_val;
 
     // ---- stage the resident queries into tensor memory (warpgroup 0: one warp per lane quadrant).
@@ -364,31 +383,38 @@ flmr_scan_kernel(const __grid_constant__ CUtensorMap tmap_d, const ScanParams p)
 
     // (stage, phase) of accumulator index a_prev in the MMA issue order; advanced by index deltas
     uint32_t as = 0, aph = 0, a_prev = 0;
-
-    uint32_t mask_next = 0;
-    int32_t fpid_next = 0;
-    if (n_tiles > 0) {
-      mask_next = __ldg(p.tile_end_mask + tile_base);
-      fpid_next = __ldg(p.tile_first_pid + tile_base);
-    }
-    for (int t = 0; t < n_tiles; ++t) {
-      const uint32_t mask = mask_next;
-      const int32_t first_pid = fpid_next;
-      if (t + 1 < n_tiles) {
-        mask_next = __ldg(p.tile_end_mask + tile_base + t + 1);
-        fpid_next = __ldg(p.tile_first_pid + tile_base + t + 1);
-      }
-      const uint32_t ep_mask = (p.debug_mode == 2) ? 0u : mask;
+    const int n_tiles_epi = (p.debug_mode >= 4) ? 0 : n_tiles;  // modes 4/5: epilogue idle
+    uint32_t mask_next = (n_tiles_epi > 0) ? __ldg(p.tile_end_mask + tile_base) : 0u;
+    for (int t = 0; t < n_tiles_epi; ++t) {
+      const uint32_t mask = (p.debug_mode == 2) ? 0u : mask_next;
+      if (t + 1 < n_tiles_epi) mask_next = __ldg(p.tile_end_mask + tile_base + t + 1);
       const int buf = t & 1;
+      // the reducers must have consumed the partial sums of tile t-2 before this buffer is reused
+      mbar_wait(bar_p_empty(buf), ((static_cast<uint32_t>(t) >> 1) & 1u) ^ 1u, p.status,
+                kDevTimeoutEpilogue, p.timeout_ns);
+      const uint32_t a_first = static_cast<uint32_t>(t) * n_mtiles;
 #pragma unroll 1
-      for (int mt = wg; mt < n_mtiles; mt += 2) {
-        const uint32_t a = static_cast<uint32_t>(t) * n_mtiles + mt;
+      for (uint32_t a = a_first + ((a_first ^ static_cast<uint32_t>(wg)) & 1u); a < a_first + n_mtiles;
+           a += 2) {
+        const int mt = static_cast<int>(a - a_first);
         as += a - a_prev;
         a_prev = a;
         while (as >= acc_stages) {
           as -= acc_stages;
           aph ^= 1u;
         }
+        // running max handed over by whoever drained (t-1, mt)
+        if (lane == 0) {
+          uint32_t spins = 0;
+          while (carry_ver[mt * 4] < static_cast<uint32_t>(t)) {
+            if (++spins > (1u << 28)) {
+              if (p.status) *reinterpret_cast<volatile int*>(p.status) = kDevTimeoutEpilogue;
+              __trap();
+            }
+          }
+        }
+        __syncwarp();
+        __threadfence_block();
         float m = carry[mt * kTileM];
         mbar_wait(bar_t_full(as), aph, p.status, kDevTimeoutEpilogue, p.timeout_ns);
         tc_fence_after_sync();
@@ -398,77 +424,113 @@ flmr_scan_kernel(const __grid_constant__ CUtensorMap tmap_d, const ScanParams p)
           if (lane == 0) mbar_arrive(bar_t_empty(as));
         } else {
           const uint32_t taddr = tmem_base + lane_base + acc_col0 + as * kTileN;
-          uint32_t v0[32], v1[32], v2[32];
-          FLMR_TMEM_LD32(v0, taddr);
-          FLMR_TMEM_LD32(v1, taddr + 32);
-          FLMR_TMEM_LD32(v2, taddr + 64);
-          FLMR_TMEM_WAIT_LD32(v0);
-          FLMR_TMEM_WAIT_LD32(v1);
-          FLMR_TMEM_WAIT_LD32(v2);
-          // all 96 columns are in registers: hand the TMEM stage back to the MMA warp
+          uint32_t v[kChunks][32];
+#pragma unroll
+          for (int c = 0; c < kChunks; ++c) FLMR_TMEM_LD32(v[c], taddr + 32 * c);
+#pragma unroll
+          for (int c = 0; c < kChunks; ++c) FLMR_TMEM_WAIT_LD32(v[c]);
+          // every column is in registers: hand the TMEM stage back to the MMA warp
           tc_fence_before_sync();
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_t_empty(as));
           float* partial_rb = partial + (buf * kRbMax + mt * 4 + quad) * kSlots;
           int slot = 0;
-          process_chunk(v0, ep_mask & 0xFFu, m, init, partial_rb, slot, lane);
-          process_chunk(v1, (ep_mask >> 8) & 0xFFu, m, init, partial_rb, slot, lane);
-          process_chunk(v2, (ep_mask >> 16) & 0xFFu, m, init, partial_rb, slot, lane);
+#pragma unroll
+          for (int c = 0; c < kChunks; ++c)
+            process_chunk(v[c], (mask >> (8 * c)) & 0xFFu, m, init, partial_rb, slot, lane);
         }
         carry[mt * kTileM] = m;
+        __threadfence_block();
+        __syncwarp();
+        if (lane == 0) carry_ver[mt * 4] = static_cast<uint32_t>(t) + 1u;
       }
-      // all row blocks of this D tile have written their partials
-      named_bar_sync(1, kEpiThreads);
-
-      // ---- finalize: per (query, passage ending in this tile); lane = passage slot ----
+      // this warp's partial sums of tile t are written (lane 0 wrote them; arrive = release)
+      if (lane == 0) mbar_arrive(bar_p_full(buf));
+    }
+    tc_fence_before_sync();
+  } else {
+    // ===================== reducers: score finalisation + per-CTA top-k =====================
+    // Per D tile and per (query, passage ending in the tile): sum the row-block partials in fixed
+    // order (deterministic), add/store partial scores if requested, offer to the top-k list.
+    const int rw = warp - (2 + kEpiWarps);  // reducer 0..kRedWarps-1 owns queries b = rw (mod kRedWarps)
+    const float* partial = reinterpret_cast<const float*>(smem + S::kOffPartial);
+    uint64_t* keys = reinterpret_cast<uint64_t*>(smem + S::kOffKeys);
+    uint64_t* minkey_s = reinterpret_cast<uint64_t*>(smem + S::kOffMinKey);
+    int* minpos_s = reinterpret_cast<int*>(smem + S::kOffMinPos);
+    const int n_tiles_red = (p.debug_mode >= 4) ? 0 : n_tiles;
+    uint32_t mask_next = 0;
+    int32_t fpid_next = 0;
+    if (n_tiles_red > 0) {
+      mask_next = __ldg(p.tile_end_mask + tile_base);
+      fpid_next = __ldg(p.tile_first_pid + tile_base);
+    }
+    for (int t = 0; t < n_tiles_red; ++t) {
+      const uint32_t mask = mask_next;
+      const int32_t first_pid = fpid_next;
+      if (t + 1 < n_tiles_red) {
+        mask_next = __ldg(p.tile_end_mask + tile_base + t + 1);
+        fpid_next = __ldg(p.tile_first_pid + tile_base + t + 1);
+      }
+      const int buf = t & 1;
+      mbar_wait(bar_p_full(buf), (static_cast<uint32_t>(t) >> 1) & 1u, p.status, kDevTimeoutEpilogue,
+                p.timeout_ns);
       const int n_slots = __popc(mask);
+      if (n_slots > 0) {
+        // work items = (owned query, passage slot) pairs, flattened over the lanes
+        const int n_own = (p.nq_pass - rw + kRedWarps - 1) / kRedWarps;
+        const int n_items = n_own * n_slots;
 #pragma unroll 1
-      for (int b = ew; b < p.nq_pass; b += kEpiWarps) {
-        uint64_t minkey = minkey_s[b];
-        int minpos = minpos_s[b];
-        bool dirty = false;
-        const bool valid = lane < n_slots;
-        float sc = 0.f;
-        uint64_t key = 0ull;
-        if (valid) {
-          const float* pr = partial + (buf * kRbMax + b * p.rbq) * kSlots + lane;
+        for (int j0 = 0; j0 < n_items; j0 += 32) {
+          const int j = j0 + lane;
+          const bool valid = j < n_items;
+          const int qi = valid ? j / n_slots : 0;
+          const int slot = j - qi * n_slots;
+          const int b = rw + qi * kRedWarps;
+          float sc = 0.f;
+          uint64_t key = 0ull;
+          if (valid) {
+            const float* pr = partial + (buf * kRbMax + b * p.rbq) * kSlots + slot;
 #pragma unroll 2
-          for (int r = 0; r < p.rbq; ++r) sc += pr[r * kSlots];
-          const int64_t pid = static_cast<int64_t>(first_pid) + lane;
-          const int64_t gi = static_cast<int64_t>(b) * p.n_passages + pid;
-          if (p.acc_in) sc += __ldg(p.acc_in + gi);
-          if (p.acc_out) p.acc_out[gi] = sc;
-          key = (static_cast<uint64_t>(float_to_ordered(sc)) << 32) |
-                static_cast<uint64_t>(0xFFFFFFFFu - static_cast<uint32_t>(pid));
-        }
-        if (p.k > 0) {
-          uint32_t hits = __ballot_sync(0xffffffffu, valid && key > minkey);
-          while (hits) {
-            const int src = __ffs(hits) - 1;
-            hits &= hits - 1;
-            const uint64_t cand = shfl64(key, src);
-            if (cand > minkey) {
-              topk_replace_min(keys + b * kMaxK, p.k, cand, minkey, minpos, lane);
-              dirty = true;
+            for (int r = 0; r < p.rbq; ++r) sc += pr[r * kSlots];
+            const int64_t pid = static_cast<int64_t>(first_pid) + slot;
+            const int64_t gi = static_cast<int64_t>(b) * p.n_passages + pid;
+            if (p.acc_in) sc += __ldg(p.acc_in + gi);
+            if (p.acc_out) p.acc_out[gi] = sc;
+            key = (static_cast<uint64_t>(float_to_ordered(sc)) << 32) |
+                  static_cast<uint64_t>(0xFFFFFFFFu - static_cast<uint32_t>(pid));
+          }
+          if (p.k > 0) {
+            uint32_t hits = __ballot_sync(0xffffffffu, valid && key > minkey_s[b]);
+            while (hits) {  // rare after warm-up: one list update at a time
+              const int src = __ffs(hits) - 1;
+              hits &= hits - 1;
+              const uint64_t cand = shfl64(key, src);
+              const int cb = __shfl_sync(0xffffffffu, b, src);
+              uint64_t minkey = minkey_s[cb];
+              int minpos = minpos_s[cb];
+              if (cand > minkey) {
+                topk_replace_min(keys + cb * kMaxK, p.k, cand, minkey, minpos, lane);
+                if (lane == 0) {
+                  minkey_s[cb] = minkey;
+                  minpos_s[cb] = minpos;
+                }
+                __syncwarp();
+              }
             }
           }
         }
-        if (dirty && lane == 0) {
-          minkey_s[b] = minkey;
-          minpos_s[b] = minpos;
-        }
       }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_p_empty(buf));
     }
-
     // ---- publish this CTA's candidates ----
     if (p.k > 0) {
       __syncwarp();
-      for (int b = ew; b < p.nq_pass; b += kEpiWarps) {
+      for (int b = rw; b < p.nq_pass; b += kRedWarps) {
         uint64_t* dst = p.cand_keys + (static_cast<int64_t>(cta) * p.nq_pass + b) * p.k;
         for (int i = lane; i < p.k; i += 32) dst[i] = keys[b * kMaxK + i];
       }
     }
-    tc_fence_before_sync();
   }
 
   // ---- teardown -----------------------------------------------------------------------------------
