@@ -214,8 +214,9 @@ __global__ void __launch_bounds__(kScanThreads, 1)
 flmr_scan_kernel(const __grid_constant__ CUtensorMap tmap_d, const ScanParams p) {
   using S = ScanSmem;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~static_cast<uintptr_t>(1023));
+  // 1024-B alignment by pointer arithmetic on the __shared__ array (keeps the shared address space
+  // visible to the compiler: LDS/STS instead of generic loads/stores)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const uint32_t smem_base = smem_u32(smem);
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
