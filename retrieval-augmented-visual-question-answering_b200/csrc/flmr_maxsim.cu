@@ -449,6 +449,24 @@ int run_search(const flmr_corpus* c, flmr_workspace* ws, const void* d_q, int n_
   p.status = ws->d_status;
   p.timeout_ns = 4000000000ull;
   if (const char* e = getenv("FLMR_DEBUG_MODE")) p.debug_mode = atoi(e);
+  if (p.debug_mode == 6) {  // timestamps of CTA 0's accumulator hand-offs, dumped by the caller
+    static long long* d_ts = nullptr;
+    if (!d_ts) {
+      FLMR_CUDA(cudaMallocManaged(reinterpret_cast<void**>(&d_ts), 64 * 8 * sizeof(long long)));
+      memset(d_ts, 0, 64 * 8 * sizeof(long long));
+    }
+    p.dbg_ts = d_ts;
+    if (const char* f = getenv("FLMR_DEBUG_TS_DUMP")) {   // dump what the PREVIOUS launch recorded
+      cudaDeviceSynchronize();
+      if (FILE* fp = fopen(f, "w")) {
+        for (int a = 0; a < 64; ++a) {
+          for (int i = 0; i < 8; ++i) fprintf(fp, "%lld ", d_ts[a * 8 + i]);
+          fprintf(fp, "\n");
+        }
+        fclose(fp);
+      }
+    }
+  }
   if (const char* e = getenv("FLMR_WATCHDOG_MS")) p.timeout_ns = strtoull(e, nullptr, 10) * 1000000ull;
 
   const int rbq_total = (nq + 31) / 32;
