@@ -375,9 +375,12 @@ void build_partition(const std::vector<int64_t>& poff, int n_ctas, int tile_n,
 
 int launch_scan(const flmr_corpus* c, flmr_workspace* ws, const ScanParams& p, cudaStream_t st) {
   static bool attr_set[64] = {};
-  auto kern = flmr_scan_kernel;
+  // product instantiation unless a timing experiment / timestamp mode was requested
+  auto kern = p.debug_mode ? flmr_scan_kernel<true> : flmr_scan_kernel<false>;
   if (c->device < 64 && !attr_set[c->device]) {
-    FLMR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    FLMR_CUDA(cudaFuncSetAttribute(flmr_scan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   ScanSmem::kBytes));
+    FLMR_CUDA(cudaFuncSetAttribute(flmr_scan_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    ScanSmem::kBytes));
     attr_set[c->device] = true;
   }

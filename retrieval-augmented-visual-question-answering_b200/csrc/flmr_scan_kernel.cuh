@@ -102,9 +102,12 @@ struct ScanParams {
 };
 
 constexpr uint32_t kDbgAcc0 = 2000;  // first accumulator index recorded in debug_mode 6
+template <bool kDebug>
 __device__ __forceinline__ void dbg_stamp(const ScanParams& p, int cta, uint32_t a, int slot) {
-  if (p.debug_mode == 6 && cta == 0 && a >= kDbgAcc0 && a < kDbgAcc0 + 64)
-    p.dbg_ts[(a - kDbgAcc0) * 8 + slot] = clock64();
+  if constexpr (kDebug) {
+    if (p.debug_mode == 6 && cta == 0 && a >= kDbgAcc0 && a < kDbgAcc0 + 64)
+      p.dbg_ts[(a - kDbgAcc0) * 8 + slot] = clock64();
+  }
 }
 
 struct ScanSmem {
@@ -236,8 +239,12 @@ __device__ __noinline__ void topk_replace_min(uint64_t* keys, int k, uint64_t ca
 }
 
 // ---- the kernel -------------------------------------------------------------------------------
+// kDebug = false is the product instantiation: no timing-experiment branches, no timestamps in the
+// hot loops (the epilogue is bound by instruction issue slots, every instruction there counts).
+template <bool kDebug>
 __global__ void __launch_bounds__(kScanThreads, 1)
 flmr_scan_kernel(const __grid_constant__ CUtensorMap tmap_d, const ScanParams p) {
+  const int dbg = kDebug ? p.debug_mode : 0;
   using S = ScanSmem;
   extern __shared__ uint8_t smem_raw[];
   // 1024-B alignment by pointer arithmetic on the __shared__ array (keeps the shared address space
@@ -268,7 +275,8 @@ flmr_scan_kernel(const __grid_constant__ CUtensorMap tmap_d, const ScanParams p)
   const int64_t tile_base = p.cta_tile_base[cta];
   const int n_tiles = static_cast<int>(p.cta_tile_base[cta + 1] - tile_base);
   const int n_mtiles = p.n_mtiles;
-  const uint32_t acc_stages = static_cast<uint32_t>(scan_acc_stages(n_mtiles));
+  const uint32_t acc_stages = static_cast<uint32_t>(scan_acc_stages(n_mtiles));   // 2 or 4
+  const uint32_t stage_mask = acc_stages - 1u, stage_shift = (acc_stages == 4u) ? 2u : 1u;
   const uint32_t acc_col0 = static_cast<uint32_t>(kQCols * n_mtiles);
 
   // ---- one-time setup --------------------------------------------------------------------------
@@ -341,7 +349,6 @@ flmr_scan_kernel(const __grid_constant__ CUtensorMap tmap_d, const ScanParams p)
     constexpr uint32_t idesc = make_idesc_bf16_f32(kTileM, kTileN);
     mbar_wait(bar_q_full, 0, p.status, kDevTimeoutMma, p.timeout_ns);  // queries are in TMEM
     tc_fence_after_sync();
-    uint32_t as = 0, aph = 0, a_prev = 0;  // (stage, phase) of accumulator a_prev
     for (int t = 0; t < n_tiles; ++t) {
       const int s = t % kDStages;
       const uint32_t ph = (t / kDStages) & 1;
@@ -352,21 +359,16 @@ flmr_scan_kernel(const __grid_constant__ CUtensorMap tmap_d, const ScanParams p)
 #pragma unroll 1
       for (uint32_t a = a_first + ((a_first ^ iw) & 1u); a < a_first + n_mtiles; a += 2) {
         const uint32_t mt = a - a_first;
-        as += a - a_prev;
-        a_prev = a;
-        while (as >= acc_stages) {
-          as -= acc_stages;
-          aph ^= 1u;
-        }
-        if (p.debug_mode != 4 && p.debug_mode != 5) {  // (modes 4/5: never wait for the epilogue)
+        const uint32_t as = a & stage_mask, aph = (a >> stage_shift) & 1u;  // TMEM stage / phase
+        if (dbg != 4 && dbg != 5) {  // (modes 4/5: never wait for the epilogue)
           mbar_wait(bar_t_empty(as), aph ^ 1u, p.status, kDevTimeoutMma, p.timeout_ns);
           tc_fence_after_sync();
         }
         const uint32_t d_tmem = tmem_base + acc_col0 + as * kTileN;
         const uint32_t a_tmem = tmem_base + mt * kQCols;
         if (elect_one_sync()) {
-          dbg_stamp(p, cta, a, 0);  // stage free, about to issue
-          if (p.debug_mode != 3) {
+          dbg_stamp<kDebug>(p, cta, a, 0);  // stage free, about to issue
+          if (dbg != 3) {
 #pragma unroll
             for (int k = 0; k < kDim / 16; ++k) {
               // advance the start-address field (16-byte units) inside the descriptor
@@ -375,8 +377,8 @@ flmr_scan_kernel(const __grid_constant__ CUtensorMap tmap_d, const ScanParams p)
               tc_mma_ts(d_tmem, a_tmem + k * 8, b_desc, idesc, k > 0 ? 1u : 0u);
             }
           }
-          if (p.debug_mode != 5) tc_commit(bar_t_full(as));  // accumulator complete -> epilogue
-          dbg_stamp(p, cta, a, 1);  // MMAs + commit issued
+          if (dbg != 5) tc_commit(bar_t_full(as));  // accumulator complete -> epilogue
+          dbg_stamp<kDebug>(p, cta, a, 1);  // MMAs + commit issued
         }
         __syncwarp();
       }
@@ -424,12 +426,10 @@ flmr_scan_kernel(const __grid_constant__ CUtensorMap tmap_d, const ScanParams p)
       if (lane == 0) mbar_arrive(bar_q_full);
     }
 
-    // (stage, phase) of accumulator index a_prev in the MMA issue order; advanced by index deltas
-    uint32_t as = 0, aph = 0, a_prev = 0;
-    const int n_tiles_epi = (p.debug_mode == 4 || p.debug_mode == 5) ? 0 : n_tiles;  // modes 4/5: epilogue idle
+    const int n_tiles_epi = (dbg == 4 || dbg == 5) ? 0 : n_tiles;  // modes 4/5: epilogue idle
     uint32_t mask_next = (n_tiles_epi > 0) ? __ldg(p.tile_end_mask + tile_base) : 0u;
     for (int t = 0; t < n_tiles_epi; ++t) {
-      const uint32_t mask = (p.debug_mode == 2) ? 0u : mask_next;
+      const uint32_t mask = (dbg == 2) ? 0u : mask_next;
       if (t + 1 < n_tiles_epi) mask_next = __ldg(p.tile_end_mask + tile_base + t + 1);
       const int buf = t & 1;
       // the reducers must have consumed the partial sums of tile t-2 before this buffer is reused
@@ -440,12 +440,7 @@ flmr_scan_kernel(const __grid_constant__ CUtensorMap tmap_d, const ScanParams p)
       for (uint32_t a = a_first + ((a_first ^ static_cast<uint32_t>(wg)) & 1u); a < a_first + n_mtiles;
            a += 2) {
         const int mt = static_cast<int>(a - a_first);
-        as += a - a_prev;
-        a_prev = a;
-        while (as >= acc_stages) {
-          as -= acc_stages;
-          aph ^= 1u;
-        }
+        const uint32_t as = a & stage_mask, aph = (a >> stage_shift) & 1u;  // TMEM stage / phase
         // running max handed over by whoever drained (t-1, mt): with an odd number of query tiles
         // that is the other warpgroup (mbarrier arrive/wait = release/acquire); with an even number
         // it is this very warp, and program order suffices
@@ -453,11 +448,11 @@ flmr_scan_kernel(const __grid_constant__ CUtensorMap tmap_d, const ScanParams p)
           mbar_wait(bar_carry(mt, quad), static_cast<uint32_t>(t - 1) & 1u, p.status,
                     kDevTimeoutEpilogue, p.timeout_ns);
         float m = carry[mt * kTileM];
-        if (quad == 0 && lane == 0) dbg_stamp(p, cta, a, 2);               // epilogue ready to wait
+        if (quad == 0 && lane == 0) dbg_stamp<kDebug>(p, cta, a, 2);               // epilogue ready to wait
         mbar_wait(bar_t_full(as), aph, p.status, kDevTimeoutEpilogue, p.timeout_ns);
         tc_fence_after_sync();
-        if (quad == 0 && lane == 0) dbg_stamp(p, cta, a, 3);               // accumulator visible
-        if (p.debug_mode == 1 || p.debug_mode == 3) {  // timing experiment: release unread
+        if (quad == 0 && lane == 0) dbg_stamp<kDebug>(p, cta, a, 3);               // accumulator visible
+        if (dbg == 1 || dbg == 3) {  // timing experiment: release unread
           tc_fence_before_sync();
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_t_empty(as));
@@ -469,18 +464,18 @@ flmr_scan_kernel(const __grid_constant__ CUtensorMap tmap_d, const ScanParams p)
 #pragma unroll
           for (int c = 0; c < kChunks; ++c) FLMR_TMEM_WAIT_LD32(v[c]);
           // every column is in registers: hand the TMEM stage back to the MMA warp
-          if (quad == 0 && lane == 0) dbg_stamp(p, cta, a, 4);             // TMEM read done
+          if (quad == 0 && lane == 0) dbg_stamp<kDebug>(p, cta, a, 4);             // TMEM read done
           tc_fence_before_sync();
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_t_empty(as));
-          if (quad == 0 && lane == 0) dbg_stamp(p, cta, a, 5);             // stage handed back
+          if (quad == 0 && lane == 0) dbg_stamp<kDebug>(p, cta, a, 5);             // stage handed back
           float* partial_rb = partial + (buf * kRbMax + mt * 4 + quad) * kSlots;
           int slot = 0;
 #pragma unroll
           for (int c = 0; c < kChunks; ++c)
             process_chunk(v[c], (mask >> (8 * c)) & 0xFFu, m, init, partial_rb, slot, lane);
         }
-        if (quad == 0 && lane == 0) dbg_stamp(p, cta, a, 6);               // chunk processing done
+        if (quad == 0 && lane == 0) dbg_stamp<kDebug>(p, cta, a, 6);               // chunk processing done
         carry[mt * kTileM] = m;
         if (carry_crosses) {
           __syncwarp();
@@ -500,7 +495,7 @@ flmr_scan_kernel(const __grid_constant__ CUtensorMap tmap_d, const ScanParams p)
     uint64_t* keys = reinterpret_cast<uint64_t*>(smem + S::kOffKeys);
     uint64_t* minkey_s = reinterpret_cast<uint64_t*>(smem + S::kOffMinKey);
     int* minpos_s = reinterpret_cast<int*>(smem + S::kOffMinPos);
-    const int n_tiles_red = (p.debug_mode == 4 || p.debug_mode == 5) ? 0 : n_tiles;
+    const int n_tiles_red = (dbg == 4 || dbg == 5) ? 0 : n_tiles;
     uint32_t mask_next = 0;
     int32_t fpid_next = 0;
     if (n_tiles_red > 0) {
