@@ -90,6 +90,12 @@ def cpu_reference_rate(args, target_seconds, steps=1, warmup=0):
     bounded sample of passages (the fp32 corpus would be 92 GB).  Returns dict for `cpu_baseline`."""
     import torch
     kind, fn = make_cpu_scorer()
+    # all the host threads the box has (torchrun exports OMP_NUM_THREADS=1, which would cripple the
+    # reference's pthread / MKL path: segmented_maxsim.cpp spawns at::get_num_threads() threads)
+    try:
+        torch.set_num_threads(max(torch.get_num_threads(), len(os.sched_getaffinity(0))))
+    except Exception:
+        pass
     cores = torch.get_num_threads()
     g = torch.Generator().manual_seed(0)
     Q = torch.nn.functional.normalize(torch.randn(args.nq, 128, generator=g), dim=-1).bfloat16().float()
@@ -319,9 +325,16 @@ def run_ours(args):
         scan_avg_ms = r_dev["scan_ms"] / max(r_dev["scan_n"], 1)
         ach_tf = flops_launch / (scan_avg_ms * 1e-3) / 1e12 if scan_avg_ms > 0 else 0.0
         ach_gbs = bytes_launch / (scan_avg_ms * 1e-3) / 1e9 if scan_avg_ms > 0 else 0.0
+        # DRAM traffic of one launch from the committed `ncu --set full` capture at this exact size
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+        if os.path.exists(tpath) and world == 1 and (n_total, nd, nq) == (1_000_000, 180, 320) and q_per_launch == 2:
+            with open(tpath) as f:
+                traffic = json.load(f).get("traffic_bytes_per_launch")
         roofline = {
             "bound": "tensor", "achieved": ach_tf, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
-            "frac": ach_tf / peaks["bf16_sustained"], "traffic": None,
+            "frac": ach_tf / peaks["bf16_sustained"], "traffic": traffic,
+            "traffic_source": "profiles/r01_ncu_scan_kernel.md (dram__bytes_read.sum + dram__bytes_write.sum, bytes per launch)" if traffic else None,
             "peak_source": peaks["source"] + " (sustained cuBLAS bf16: kernel timed inside a long step)",
             "kernel": "flmr_scan_kernel", "launch_ms": scan_avg_ms, "launches_timed": r_dev["scan_n"],
             "scan_share_of_step": r_dev["scan_ms"] / r_dev["dev_ms"] if r_dev["dev_ms"] > 0 else None,
