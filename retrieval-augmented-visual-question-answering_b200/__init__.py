@@ -8,5 +8,6 @@ __all__ = ["FlatCorpus", "maxsim_scores", "maxsim_topk", "topk_merge", "debug_sc
 from .searcher import Searcher, Ranking  # noqa: F401,E402
 from .sharded import ShardedSearcher, shard_ranges  # noqa: F401,E402
 from .index_io import save_flat_index, load_flat_index  # noqa: F401,E402
+from .indexer import Indexer  # noqa: F401,E402
 
-__all__ += ["Searcher", "Ranking", "ShardedSearcher", "shard_ranges", "save_flat_index", "load_flat_index"]
+__all__ += ["Searcher", "Ranking", "ShardedSearcher", "shard_ranges", "save_flat_index", "load_flat_index", "Indexer"]

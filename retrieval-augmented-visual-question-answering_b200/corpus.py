@@ -75,6 +75,28 @@ class FlatCorpus:
         self._ws = None
         self.pid_base = int(pid_base)
 
+    @classmethod
+    def from_index(cls, path: str, device=None, rank: int = 0, world_size: int = 1) -> "FlatCorpus":
+        """Load a flat index (index_io.py) — or, with world_size > 1, only this rank's contiguous,
+        token-balanced passage shard of it — into HBM."""
+        import json
+        import os
+        from .index_io import load_flat_index
+        from .sharded import shard_ranges
+        if world_size == 1:
+            tokens, doclens, _ = load_flat_index(path)
+            return cls(tokens, doclens, device=device)
+        with open(os.path.join(path, "metadata.json")) as f:
+            meta = json.load(f)
+        if meta.get("num_chunks", 0) == 0:
+            all_doclens = np.load(os.path.join(path, "doclens.npy"))
+        else:
+            all_doclens = np.concatenate([np.load(os.path.join(path, "doclens.%d.npy" % c))
+                                          for c in range(meta["num_chunks"])])
+        p0, p1 = shard_ranges(all_doclens, world_size)[rank]
+        tokens, doclens, _ = load_flat_index(path, passage_range=(p0, p1))
+        return cls(tokens, doclens, device=device, pid_base=p0)
+
     # -- properties ---------------------------------------------------------------------------
     @property
     def n_passages(self) -> int:

@@ -1,0 +1,111 @@
+"""``Indexer`` with the call surface of the reference's ``colbert.Indexer``
+(third_party/ColBERT/colbert/indexer.py:15-84) that writes the FLAT store the scan kernel streams,
+instead of a PLAID index (k-means centroids + residual codes + IVF,
+colbert/indexing/collection_indexer.py:56-73).  This is the step *before* the hot path
+(SURVEY.md 8f-1): the document encoder stays PyTorch and is passed in as ``encode_fn``.
+
+    indexer = Indexer(checkpoint=..., config=..., encode_fn=lambda passages: (embs [T, d], doclens))
+    path = indexer.index(name="temp_index.nbits=8", collection=passages, overwrite=True)
+
+``encode_fn`` has the contract of ``CollectionEncoder.encode_passages``
+(colbert/indexing/collection_encoder.py:13-45): a list of passages -> (packed embeddings, doclens).
+Chunks of 25,000 passages (colbert/data/collection.py:77-78) are owned round-robin by ranks
+(collection.py:58-75), written by a background saver thread through a bounded queue
+(index_saver.py:52-73), and skipped when already complete under ``overwrite='resume'``
+(index_saver.py:30-50, collection_indexer.py:325-327).
+"""
+from __future__ import annotations
+
+import os
+import queue
+import threading
+from typing import Callable, Optional, Sequence
+
+import torch
+
+from .index_io import chunk_exists, finalize_chunked_index, save_flat_chunk
+
+
+class Indexer:
+    def __init__(self, checkpoint=None, config=None, encode_fn: Optional[Callable] = None,
+                 index_root: Optional[str] = None, chunksize: int = 25_000, rank: int = 0, nranks: int = 1):
+        self.checkpoint = checkpoint
+        self.config = config
+        self.encode_fn = encode_fn
+        self.index_root = index_root or (getattr(config, "index_root_", None) if config is not None else None)
+        self.chunksize = int(chunksize)
+        self.rank, self.nranks = int(rank), int(nranks)
+        self.index_path = None
+
+    def get_index(self):
+        return self.index_path
+
+    def erase(self):
+        """colbert.Indexer.erase (indexer.py:33-56): delete the index files already at index_path."""
+        assert self.index_path is not None
+        deleted = []
+        for fn in sorted(os.listdir(self.index_path)):
+            if fn.endswith((".bf16", ".npy", ".json", ".tmp")):
+                os.remove(os.path.join(self.index_path, fn))
+                deleted.append(fn)
+        return deleted
+
+    def _path(self, name: str) -> str:
+        return name if (os.path.isabs(name) or self.index_root is None) else os.path.join(self.index_root, name)
+
+    def index(self, name: str, collection: Sequence, overwrite=False) -> str:
+        assert overwrite in [True, False, "reuse", "resume"]
+        if self.encode_fn is None:
+            raise RuntimeError("Indexer needs encode_fn=...: the document encoder (ColBERT.doc / "
+                               "Checkpoint.docFromText) stays in PyTorch and is out of scope here")
+        self.index_path = self._path(name)
+        exists = os.path.exists(os.path.join(self.index_path, "metadata.json")) or (
+            os.path.isdir(self.index_path) and len(os.listdir(self.index_path)) > 0)
+        assert overwrite in [True, "reuse", "resume"] or not exists, self.index_path
+        os.makedirs(self.index_path, exist_ok=True)
+        if overwrite is True and self.rank == 0:
+            self.erase()
+        if exists and overwrite == "reuse" and os.path.exists(os.path.join(self.index_path, "metadata.json")):
+            return self.index_path
+        self._encode(collection, resume=(overwrite == "resume"))
+        return self.index_path
+
+    # -- encode -> compress(no-op: bf16) -> save, chunk by chunk ---------------------------------------
+    def _encode(self, collection: Sequence, resume: bool) -> None:
+        n = len(collection)
+        chunksize = min(self.chunksize, 1 + n // self.nranks)       # Collection.get_chunksize
+        num_chunks = (n + chunksize - 1) // chunksize
+        q: "queue.Queue" = queue.Queue(maxsize=3)                     # IndexSaver.thread (index_saver.py:52-66)
+        errors = []
+
+        def saver():
+            for item in iter(q.get, None):
+                try:
+                    save_flat_chunk(self.index_path, *item)
+                except Exception as e:   # surfaced after join
+                    errors.append(e)
+
+        th = threading.Thread(target=saver)
+        th.start()
+        try:
+            for c in range(num_chunks):
+                if c % self.nranks != self.rank:                       # round-robin chunk ownership
+                    continue
+                if resume and chunk_exists(self.index_path, c):
+                    continue
+                p0, p1 = c * chunksize, min(n, (c + 1) * chunksize)
+                embs, doclens = self.encode_fn(list(collection[p0:p1]))
+                embs = torch.as_tensor(embs)
+                if len(doclens) != p1 - p0 or int(sum(doclens)) != embs.size(0):
+                    raise ValueError("encode_fn returned %d doclens / %d embeddings for %d passages"
+                                     % (len(doclens), embs.size(0), p1 - p0))
+                q.put((c, p0, embs.detach().to("cpu", torch.bfloat16), list(doclens)))
+        finally:
+            q.put(None)
+            th.join()
+        if errors:
+            raise errors[0]
+        if torch.distributed.is_available() and torch.distributed.is_initialized() and self.nranks > 1:
+            torch.distributed.barrier()
+        if self.rank == 0:
+            finalize_chunked_index(self.index_path, num_chunks)
