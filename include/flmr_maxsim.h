@@ -145,6 +145,22 @@ int flmr_topk_merge(const float* d_in_scores, const int64_t* d_in_pids, int n_li
                     int k_in, int k_out, float* d_out_scores, int64_t* d_out_pids, int device,
                     void* stream);
 
+/*
+ * Decode a chunk of a PLAID (ColBERTv2 residual-compressed) index into bf16 token embeddings,
+ * so existing reference indexes can be scanned without re-encoding.  Replaces
+ * decompress_residuals_cpp (CB/search/decompress_residuals.cpp:80-155), its CUDA twin
+ * (CB/indexing/codecs/decompress_residuals.cu:8-75) and the F.normalize that follows
+ * (CB/search/index_storage.py:173).  Synchronous on `stream` (validates the centroid codes).
+ *   d_codes      int32 [n_tokens]            nearest-centroid id per token   (<c>.codes.pt)
+ *   d_residuals  uint8 [n_tokens, dim*nbits/8] packed bucket indices         (<c>.residuals.pt)
+ *   d_centroids  fp32  [n_centroids, dim]    (centroids.pt, upcast)
+ *   d_bucket_weights fp32 [2^nbits]          (buckets.pt[1])
+ *   d_out_bf16   bf16  [n_tokens, dim]       = normalize(centroids[code] + weights[idx]) if normalize
+ */
+int flmr_plaid_decode(const int32_t* d_codes, const uint8_t* d_residuals, int64_t n_tokens,
+                      const float* d_centroids, int64_t n_centroids, const float* d_bucket_weights,
+                      int nbits, int dim, int normalize, void* d_out_bf16, int device, void* stream);
+
 /* Test infrastructure: plain SIMT fp32 MaxSim of every passage (same contract as
  * flmr_maxsim_scores), independent of the tensor-core kernel. */
 int flmr_debug_maxsim_scores_simt(const flmr_corpus_t* corpus, const void* d_q, int n_queries,

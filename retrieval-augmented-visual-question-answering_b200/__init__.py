@@ -9,5 +9,8 @@ from .searcher import Searcher, Ranking  # noqa: F401,E402
 from .sharded import ShardedSearcher, shard_ranges  # noqa: F401,E402
 from .index_io import save_flat_index, load_flat_index  # noqa: F401,E402
 from .indexer import Indexer  # noqa: F401,E402
+from .modeling import (FLMRModelForRetrieval, all_pairs_maxsim, colbert_score,  # noqa: F401,E402
+                       in_batch_negatives_loss)
 
-__all__ += ["Searcher", "Ranking", "ShardedSearcher", "shard_ranges", "save_flat_index", "load_flat_index", "Indexer"]
+__all__ += ["Searcher", "Ranking", "ShardedSearcher", "shard_ranges", "save_flat_index", "load_flat_index", "Indexer",
+            "FLMRModelForRetrieval", "all_pairs_maxsim", "colbert_score", "in_batch_negatives_loss"]

@@ -97,6 +97,13 @@ class FlatCorpus:
         tokens, doclens, _ = load_flat_index(path, passage_range=(p0, p1))
         return cls(tokens, doclens, device=device, pid_base=p0)
 
+    @classmethod
+    def from_plaid(cls, path: str, device=None) -> "FlatCorpus":
+        """Decode a reference PLAID index directory on the GPU (plaid.py) and keep it resident."""
+        from .plaid import plaid_to_flat
+        tokens, doclens = plaid_to_flat(path, device)
+        return cls(tokens, doclens, device=tokens.device)
+
     # -- properties ---------------------------------------------------------------------------
     @property
     def n_passages(self) -> int:

@@ -178,6 +178,60 @@ __global__ void flmr_simt_maxsim_kernel(const __nv_bfloat16* __restrict__ d, con
   if (threadIdx.x == 0) out[static_cast<int64_t>(b) * n_passages + p] = red[0];
 }
 
+// PLAID residual decode: emb[t][i] = centroids[code[t]][i] + bucket_weights[idx(t, i)],
+// idx = the nbits-wide field of dim i in the token's packed residual bytes, bit-reversed (the
+// reference packs each bucket index LSB-first into big-endian bytes: residual.py:188-204 binarize,
+// :51-73 reversed_bit_map, :77-93 lookup table; decode loop decompress_residuals.cpp:27-78), then the
+// row is L2-normalised (index_storage.py:173) and stored as bf16.  HBM-bound byte work: one warp per
+// token, lane = 4 dims, centroid rows come from L2, bucket weights from shared memory.
+__global__ void flmr_plaid_decode_kernel(const int32_t* __restrict__ codes,
+                                         const uint8_t* __restrict__ residuals,
+                                         const float* __restrict__ centroids,
+                                         const float* __restrict__ bucket_weights, int nbits,
+                                         int normalize, int64_t n_tokens, int64_t n_centroids,
+                                         uint2* __restrict__ out, int* __restrict__ bad_code) {
+  __shared__ float s_w[256];
+  for (int i = threadIdx.x; i < (1 << nbits); i += blockDim.x) s_w[i] = bucket_weights[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  const int keys = 8 / nbits;                 // bucket indices per packed byte
+  const int packed_dim = kDim * nbits / 8;    // bytes per token
+  const uint32_t mask = (1u << nbits) - 1u;
+  for (int64_t t = warp0; t < n_tokens; t += n_warps) {
+    const int32_t code = codes[t];
+    if (code < 0 || code >= n_centroids) {    // corrupt index: flag, never read out of bounds
+      if (lane == 0) *bad_code = 1;
+      continue;
+    }
+    const float4 c = __ldg(reinterpret_cast<const float4*>(centroids + static_cast<int64_t>(code) * kDim) + lane);
+    const uint8_t* row = residuals + t * packed_dim;
+    float v[4] = {c.x, c.y, c.z, c.w};
+#pragma unroll
+    for (int dd = 0; dd < 4; ++dd) {
+      const int i = 4 * lane + dd;
+      const uint32_t byte = __ldg(row + i / keys);
+      const uint32_t field = (byte >> (8 - nbits * (i % keys + 1))) & mask;
+      v[dd] += s_w[__brev(field) >> (32 - nbits)];
+    }
+    if (normalize) {
+      float ss = v[0] * v[0] + v[1] * v[1] + v[2] * v[2] + v[3] * v[3];
+#pragma unroll
+      for (int off = 16; off >= 1; off >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, off);
+      const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);   // torch.nn.functional.normalize eps
+#pragma unroll
+      for (int dd = 0; dd < 4; ++dd) v[dd] *= inv;
+    }
+    __nv_bfloat162 lo = __floats2bfloat162_rn(v[0], v[1]);
+    __nv_bfloat162 hi = __floats2bfloat162_rn(v[2], v[3]);
+    uint2 w;
+    w.x = *reinterpret_cast<uint32_t*>(&lo);
+    w.y = *reinterpret_cast<uint32_t*>(&hi);
+    out[t * 32 + lane] = w;
+  }
+}
+
 // Candidate merge: per query, select the k_out best of n candidates by (score desc, pid asc).
 // Candidates come either as packed keys written by the scan kernel (keys != null; pid = pid_base +
 // ~low32) or as (score, pid) arrays laid out [list][query][k_in].  One 1024-thread block per query,
@@ -792,6 +846,41 @@ int flmr_topk_merge(const float* d_in_scores, const int64_t* d_in_pids, int n_li
       nullptr, d_in_scores, d_in_pids, n_lists, n_queries, k_in, k_out, 0, d_out_scores, d_out_pids);
   FLMR_CUDA(cudaGetLastError());
   ++g_launches;
+  return FLMR_OK;
+}
+
+int flmr_plaid_decode(const int32_t* d_codes, const uint8_t* d_residuals, int64_t n_tokens,
+                      const float* d_centroids, int64_t n_centroids, const float* d_bucket_weights,
+                      int nbits, int dim, int normalize, void* d_out_bf16, int device, void* stream) {
+  if (!d_codes || !d_residuals || !d_centroids || !d_bucket_weights || !d_out_bf16)
+    return fail(FLMR_ERR_INVALID_ARG, "null pointer");
+  if (dim != kDim) return fail(FLMR_ERR_UNSUPPORTED, "dim=%d (only %d is supported)", dim, kDim);
+  if (nbits != 1 && nbits != 2 && nbits != 4 && nbits != 8)
+    return fail(FLMR_ERR_INVALID_ARG, "nbits=%d (the PLAID codec packs 1, 2, 4 or 8 bits per dim)", nbits);
+  if (n_tokens < 0 || n_centroids < 1) return fail(FLMR_ERR_INVALID_ARG, "bad sizes");
+  if (n_tokens == 0) return FLMR_OK;
+  DeviceGuard guard(device);
+  if (!guard.ok) return fail(FLMR_ERR_CUDA, "cudaSetDevice(%d) failed", device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int* d_bad = nullptr;
+  FLMR_CUDA(cudaMalloc(reinterpret_cast<void**>(&d_bad), sizeof(int)));
+  cudaError_t e = cudaMemsetAsync(d_bad, 0, sizeof(int), st);
+  const int threads = 256;
+  const int64_t want = (n_tokens * 32 + threads - 1) / threads;
+  const int blocks = static_cast<int>(std::min<int64_t>(want, 148 * 16));
+  if (e == cudaSuccess) {
+    flmr_plaid_decode_kernel<<<blocks, threads, 0, st>>>(d_codes, d_residuals, d_centroids,
+                                                       d_bucket_weights, nbits, normalize, n_tokens,
+                                                       n_centroids, static_cast<uint2*>(d_out_bf16), d_bad);
+    ++g_launches;
+    e = cudaGetLastError();
+  }
+  int bad = 0;
+  if (e == cudaSuccess) e = cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cudaFree(d_bad);
+  if (e != cudaSuccess) return fail(FLMR_ERR_CUDA, "plaid decode failed: %s", cudaGetErrorString(e));
+  if (bad) return fail(FLMR_ERR_INVALID_ARG, "a centroid code is outside [0, %lld)", (long long)n_centroids);
   return FLMR_OK;
 }
 
