@@ -505,6 +505,8 @@ int run_search(const flmr_corpus* c, flmr_workspace* ws, const void* d_q, int n_
   p.q_pad = reinterpret_cast<const uint4*>(ws->d_qpad);
   p.status = ws->d_status;
   p.timeout_ns = 4000000000ull;
+  p.lane_mode_max_rbq = 4;   // measured (profiles/r01_debug_mode_probes.log): lane-per-query wins up to 4 row blocks per query
+  if (const char* e = getenv("FLMR_LANE_RBQ")) p.lane_mode_max_rbq = atoi(e);
   if (const char* e = getenv("FLMR_DEBUG_MODE")) p.debug_mode = atoi(e);
   if (p.debug_mode == 6) {  // timestamps of CTA 0's accumulator hand-offs, dumped by the caller
     static long long* d_ts = nullptr;

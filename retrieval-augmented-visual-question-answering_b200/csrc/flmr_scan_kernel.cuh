@@ -55,6 +55,8 @@ constexpr int kSlots = kTileN / kGroup;   // passage ends per tile, at most (24 
 constexpr int kChunks = kTileN / 32;      // 32-column chunks per accumulator
 constexpr int kQCols = kDim / 2;          // TMEM columns of one query tile (bf16 pairs)
 constexpr int kMaxAccStages = 4;
+constexpr int kFastSlots = 4;             // passage ends per tile whose lane sums are left to the reducer
+constexpr int kLaneStride = 33;           // padded row of 32 lane values (conflict-free transposed reads)
 constexpr int kDStages = (kTileN == 96) ? 7 : 10;
 constexpr int kDTileBytes = kTileN * kDim * 2;   // 24 KiB: [2 k-blocks][96 rows][64 bf16]
 constexpr int kDKBlockBytes = kTileN * 128;      // 12 KiB
@@ -82,6 +84,7 @@ struct ScanParams {
   int32_t n_mtiles;                // 128-row query tiles (1..kMtMax)
   int32_t nq_pass;                 // queries resident in this pass (1..kNqMax)
   int32_t rbq;                     // 32-row blocks per query in this pass
+  int32_t lane_mode_max_rbq;       // reducer: lane-per-query summation when rbq <= this, else warp-per-item
   float init_val;                  // -inf (true max) or 0 (reference CPU "ReLU" variant)
   // score plumbing
   const float* acc_in;             // [nq_pass][n_passages] partial scores of earlier row slices, or null
@@ -115,7 +118,10 @@ struct ScanSmem {
   static constexpr int kOffD = 0;
   static constexpr int kOffPartial = kOffD + kDStages * kDTileBytes;
   static constexpr int kPartialBytes = 2 * kRbMax * kSlots * 4;
-  static constexpr int kOffKeys = kOffPartial + kPartialBytes;
+  // per-lane passage maxima of the first kFastSlots passage ends of a tile: [2][kFastSlots][kRbMax][33]
+  static constexpr int kOffLanePart = kOffPartial + kPartialBytes;
+  static constexpr int kLanePartBytes = 2 * kFastSlots * kRbMax * kLaneStride * 4;
+  static constexpr int kOffKeys = kOffLanePart + kLanePartBytes;
   static constexpr int kKeysBytes = kNqMax * kMaxK * 8;
   static constexpr int kOffMinKey = kOffKeys + kKeysBytes;           // u64[kNqMax]
   static constexpr int kOffMinPos = kOffMinKey + kNqMax * 8;         // int[kNqMax]
@@ -152,7 +158,8 @@ __device__ __forceinline__ float warp_sum(float s) {
 // either a 4-instruction fold into the running max or, per passage END in this chunk, a selected
 // tree max + one warp sum.
 __device__ __forceinline__ void process_chunk(const uint32_t (&v)[32], uint32_t bits, float& m,
-                                              float init, float* partial_rb, int& slot, int lane) {
+                                              float init, float* partial_rb, float* lane_part_rb,
+                                              int& slot, int lane) {
   if (bits == 0u) {
     // no passage ends in this chunk: fold all 32 columns into the running max (16 FMNMX3)
     float r[11];
@@ -187,8 +194,14 @@ __device__ __forceinline__ void process_chunk(const uint32_t (&v)[32], uint32_t 
     const float y = fmax3(sel[3], sel[4], sel[5]);
     float s = fmax3(m, x, y);
     s = fmax3(s, sel[6], sel[7]);
-    s = warp_sum(s);
-    if (lane == 0) partial_rb[slot] = s;
+    if (slot < kFastSlots) {
+      // common case: every lane parks its maximum, the reducer warp sums the 32 lanes later
+      // (keeps the 5-step shuffle chain off the epilogue's critical path)
+      lane_part_rb[slot * (kRbMax * kLaneStride)] = s;
+    } else {
+      s = warp_sum(s);
+      if (lane == 0) partial_rb[slot] = s;
+    }
     ++slot;
     m = init;
     live &= ~upto;
@@ -397,6 +410,7 @@ flmr_scan_kernel(const __grid_constant__ CUtensorMap tmap_d, const ScanParams p)
     const int quad = warp & 3;        // TMEM lane quadrant this warp may access
     const uint32_t lane_base = static_cast<uint32_t>(quad * 32) << 16;
     float* partial = reinterpret_cast<float*>(smem + S::kOffPartial);
+    float* lane_part = reinterpret_cast<float*>(smem + S::kOffLanePart) + lane;
     float* carry = reinterpret_cast<float*>(smem + S::kOffCarry) + quad * 32 + lane;
     const bool carry_crosses = (n_mtiles & 1) != 0;  // odd: (t, mt) and (t+1, mt) are drained by different warpgroups
     const float init = p.init_val;
@@ -460,21 +474,26 @@ flmr_scan_kernel(const __grid_constant__ CUtensorMap tmap_d, const ScanParams p)
         } else {
           const uint32_t taddr = tmem_base + lane_base + acc_col0 + as * kTileN;
           uint32_t v[kChunks][32];
+          float* partial_rb = partial + (buf * kRbMax + mt * 4 + quad) * kSlots;
+          float* lane_part_rb = lane_part + ((buf * kFastSlots) * kRbMax + mt * 4 + quad) * kLaneStride;
+          int slot = 0;
+          // chunk 0 first; the remaining chunks stream in while chunk 0 is folded
+          FLMR_TMEM_LD32(v[0], taddr);
+          FLMR_TMEM_WAIT_LD32(v[0]);
 #pragma unroll
-          for (int c = 0; c < kChunks; ++c) FLMR_TMEM_LD32(v[c], taddr + 32 * c);
+          for (int c = 1; c < kChunks; ++c) FLMR_TMEM_LD32(v[c], taddr + 32 * c);
+          process_chunk(v[0], mask & 0xFFu, m, init, partial_rb, lane_part_rb, slot, lane);
 #pragma unroll
-          for (int c = 0; c < kChunks; ++c) FLMR_TMEM_WAIT_LD32(v[c]);
-          // every column is in registers: hand the TMEM stage back to the MMA warp
+          for (int c = 1; c < kChunks; ++c) FLMR_TMEM_WAIT_LD32(v[c]);
+          // every column is in registers: hand the TMEM stage back to the MMA warps
           if (quad == 0 && lane == 0) dbg_stamp<kDebug>(p, cta, a, 4);             // TMEM read done
           tc_fence_before_sync();
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_t_empty(as));
           if (quad == 0 && lane == 0) dbg_stamp<kDebug>(p, cta, a, 5);             // stage handed back
-          float* partial_rb = partial + (buf * kRbMax + mt * 4 + quad) * kSlots;
-          int slot = 0;
 #pragma unroll
-          for (int c = 0; c < kChunks; ++c)
-            process_chunk(v[c], (mask >> (8 * c)) & 0xFFu, m, init, partial_rb, slot, lane);
+          for (int c = 1; c < kChunks; ++c)
+            process_chunk(v[c], (mask >> (8 * c)) & 0xFFu, m, init, partial_rb, lane_part_rb, slot, lane);
         }
         if (quad == 0 && lane == 0) dbg_stamp<kDebug>(p, cta, a, 6);               // chunk processing done
         carry[mt * kTileM] = m;
@@ -514,44 +533,80 @@ flmr_scan_kernel(const __grid_constant__ CUtensorMap tmap_d, const ScanParams p)
       mbar_wait(bar_p_full(buf), (static_cast<uint32_t>(t) >> 1) & 1u, p.status, kDevTimeoutEpilogue,
                 p.timeout_ns);
       const int n_slots = __popc(mask);
-      if (n_slots > 0) {
-        // work items = (owned query, passage slot) pairs, flattened over the lanes
-        const int n_own = (p.nq_pass - rw + kRedWarps - 1) / kRedWarps;
-        const int n_items = n_own * n_slots;
+      const float* lane_part0 = reinterpret_cast<const float*>(smem + S::kOffLanePart);
 #pragma unroll 1
-        for (int j0 = 0; j0 < n_items; j0 += 32) {
-          const int j = j0 + lane;
-          const bool valid = j < n_items;
-          const int qi = valid ? j / n_slots : 0;
-          const int slot = j - qi * n_slots;
-          const int b = rw + qi * kRedWarps;
-          float sc = 0.f;
-          uint64_t key = 0ull;
-          if (valid) {
-            const float* pr = partial + (buf * kRbMax + b * p.rbq) * kSlots + slot;
+      for (int slot = 0; slot < n_slots; ++slot) {
+        const int64_t pid = static_cast<int64_t>(first_pid) + slot;
+        const float* lp_slot = lane_part0 + ((buf * kFastSlots + slot) * kRbMax) * kLaneStride;
+        if (slot < kFastSlots && p.rbq <= p.lane_mode_max_rbq) {
+          // many short queries per pass: lane = query, each lane sums its query's 32 * rbq lane maxima
+          // (transposed read of the stride-33 layout: conflict-free for rbq = 1)
+#pragma unroll 1
+          for (int b0 = 0; b0 < p.nq_pass; b0 += 32) {
+            const int b = b0 + lane;
+            const bool valid = b < p.nq_pass;
+            float sc = 0.f;
+            uint64_t key = 0ull;
+            if (valid) {
+              const float* lp = lp_slot + (b * p.rbq) * kLaneStride;
+              for (int r = 0; r < p.rbq; ++r) {
+#pragma unroll 8
+                for (int j = 0; j < 32; ++j) sc += lp[r * kLaneStride + j];
+              }
+              const int64_t gi = static_cast<int64_t>(b) * p.n_passages + pid;
+              if (p.acc_in) sc += __ldg(p.acc_in + gi);
+              if (p.acc_out) p.acc_out[gi] = sc;
+              key = (static_cast<uint64_t>(float_to_ordered(sc)) << 32) |
+                    static_cast<uint64_t>(0xFFFFFFFFu - static_cast<uint32_t>(pid));
+            }
+            if (p.k > 0) {
+              uint32_t hits = __ballot_sync(0xffffffffu, valid && key > minkey_s[valid ? b : 0]);
+              while (hits) {  // rare after warm-up: one list update at a time
+                const int src = __ffs(hits) - 1;
+                hits &= hits - 1;
+                const uint64_t cand = shfl64(key, src);
+                const int cb = b0 + src;
+                uint64_t minkey = minkey_s[cb];
+                int minpos = minpos_s[cb];
+                if (cand > minkey) {
+                  topk_replace_min(keys + cb * kMaxK, p.k, cand, minkey, minpos, lane);
+                  if (lane == 0) {
+                    minkey_s[cb] = minkey;
+                    minpos_s[cb] = minpos;
+                  }
+                  __syncwarp();
+                }
+              }
+            }
+          }
+        } else {
+#pragma unroll 1
+          for (int b = 0; b < p.nq_pass; ++b) {
+            // score of (query b, passage pid): the whole warp sums the row-block partials in fixed order
+            float sc = 0.f;
+            if (slot < kFastSlots) {
+              const float* lp = lp_slot + (b * p.rbq) * kLaneStride + lane;
 #pragma unroll 2
-            for (int r = 0; r < p.rbq; ++r) sc += pr[r * kSlots];
-            const int64_t pid = static_cast<int64_t>(first_pid) + slot;
+              for (int r = 0; r < p.rbq; ++r) sc += lp[r * kLaneStride];
+              sc = warp_sum(sc);
+            } else {
+              const float* pr = partial + (buf * kRbMax + b * p.rbq) * kSlots + slot;
+#pragma unroll 2
+              for (int r = 0; r < p.rbq; ++r) sc += pr[r * kSlots];
+            }
             const int64_t gi = static_cast<int64_t>(b) * p.n_passages + pid;
             if (p.acc_in) sc += __ldg(p.acc_in + gi);
-            if (p.acc_out) p.acc_out[gi] = sc;
-            key = (static_cast<uint64_t>(float_to_ordered(sc)) << 32) |
-                  static_cast<uint64_t>(0xFFFFFFFFu - static_cast<uint32_t>(pid));
-          }
-          if (p.k > 0) {
-            uint32_t hits = __ballot_sync(0xffffffffu, valid && key > minkey_s[b]);
-            while (hits) {  // rare after warm-up: one list update at a time
-              const int src = __ffs(hits) - 1;
-              hits &= hits - 1;
-              const uint64_t cand = shfl64(key, src);
-              const int cb = __shfl_sync(0xffffffffu, b, src);
-              uint64_t minkey = minkey_s[cb];
-              int minpos = minpos_s[cb];
-              if (cand > minkey) {
-                topk_replace_min(keys + cb * kMaxK, p.k, cand, minkey, minpos, lane);
+            if (p.acc_out && lane == 0) p.acc_out[gi] = sc;
+            if (p.k > 0) {
+              const uint64_t key = (static_cast<uint64_t>(float_to_ordered(sc)) << 32) |
+                                   static_cast<uint64_t>(0xFFFFFFFFu - static_cast<uint32_t>(pid));
+              uint64_t minkey = minkey_s[b];
+              if (key > minkey) {  // warp-uniform; rare after warm-up
+                int minpos = minpos_s[b];
+                topk_replace_min(keys + b * kMaxK, p.k, key, minkey, minpos, lane);
                 if (lane == 0) {
-                  minkey_s[cb] = minkey;
-                  minpos_s[cb] = minpos;
+                  minkey_s[b] = minkey;
+                  minpos_s[b] = minpos;
                 }
                 __syncwarp();
               }
