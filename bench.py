@@ -90,10 +90,13 @@ def cpu_reference_rate(args, target_seconds, steps=1, warmup=0):
     bounded sample of passages (the fp32 corpus would be 92 GB).  Returns dict for `cpu_baseline`."""
     import torch
     kind, fn = make_cpu_scorer()
-    # all the host threads the box has (torchrun exports OMP_NUM_THREADS=1, which would cripple the
-    # reference's pthread / MKL path: segmented_maxsim.cpp spawns at::get_num_threads() threads)
+    # all the host cores the box has.  torch's default (physical cores) is the fastest setting for the
+    # reference's MKL GEMM + pthread reduction (SMT siblings slow it down: 0.0166 q/s at 64 threads vs
+    # 0.0103 at 128 on the round-1 box); torchrun exports OMP_NUM_THREADS=1, which would cripple it
+    # (segmented_maxsim.cpp spawns at::get_num_threads() threads), so undo that.
     try:
-        torch.set_num_threads(max(torch.get_num_threads(), len(os.sched_getaffinity(0))))
+        if os.environ.get("OMP_NUM_THREADS") == "1" or torch.get_num_threads() == 1:
+            torch.set_num_threads(max(1, len(os.sched_getaffinity(0)) // 2))
     except Exception:
         pass
     cores = torch.get_num_threads()
