@@ -502,7 +502,9 @@ flmr_scan_kernel(const __grid_constant__ CUtensorMap tmap_d, const ScanParams p)
           if (lane == 0) mbar_arrive(bar_carry(mt, quad));
         }
       }
-      // this warp's partial sums of tile t are written (lane 0 wrote them; arrive = release)
+      // this warp's per-lane maxima / partial sums of tile t are written: order every lane's stores
+      // before lane 0's arrive (release); the reducer's wait is the matching acquire
+      __syncwarp();
       if (lane == 0) mbar_arrive(bar_p_full(buf));
     }
     tc_fence_before_sync();
