@@ -70,8 +70,8 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 // Bounded wait: a protocol bug must surface as a trapped launch, never as a hung GPU box.
 // `status` receives `code` before the trap so the host can say which role starved.  The spinning
 // path is kept out of line so the hot loops stay small (instruction-cache footprint).
-__device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity, int* status, int code,
-                                            uint64_t timeout_ns) {
+__device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity, int* status, int code) {
+  constexpr uint64_t timeout_ns = 4000000000ull;   // 4 s of polling = a protocol bug, not a slow wait
   uint32_t spins = 0;
   uint64_t t0 = 0;
   while (!mbar_try_wait(bar, parity)) {
@@ -88,10 +88,9 @@ __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity, int* 
     }
   }
 }
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* status, int code,
-                                          uint64_t timeout_ns) {
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* status, int code) {
   if (mbar_try_wait(bar, parity)) return;
-  mbar_wait_slow(bar, parity, status, code, timeout_ns);
+  mbar_wait_slow(bar, parity, status, code);
 }
 
 // ---- TMA ----------------------------------------------------------------------------------------

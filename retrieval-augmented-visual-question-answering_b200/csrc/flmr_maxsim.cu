@@ -428,16 +428,9 @@ void build_partition(const std::vector<int64_t>& poff, int n_ctas, int tile_n,
 }
 
 int launch_scan(const flmr_corpus* c, flmr_workspace* ws, const ScanParams& p, cudaStream_t st) {
-  static bool attr_set[64] = {};
   // product instantiation unless a timing experiment / timestamp mode was requested
+  // (both instantiations got their dynamic-shared-memory limit raised in flmr_corpus_create)
   auto kern = p.debug_mode ? flmr_scan_kernel<true> : flmr_scan_kernel<false>;
-  if (c->device < 64 && !attr_set[c->device]) {
-    FLMR_CUDA(cudaFuncSetAttribute(flmr_scan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   ScanSmem::kBytes));
-    FLMR_CUDA(cudaFuncSetAttribute(flmr_scan_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   ScanSmem::kBytes));
-    attr_set[c->device] = true;
-  }
   EventPair ev{};
   if (g_profiling) {
     FLMR_CUDA(cudaEventCreate(&ev.a));
@@ -491,6 +484,11 @@ int run_search(const flmr_corpus* c, flmr_workspace* ws, const void* d_q, int n_
   if (n_queries < 0 || nq <= 0) return fail(FLMR_ERR_INVALID_ARG, "bad n_queries=%d nq=%d", n_queries, nq);
   if (k < 0 || k > kMaxK) return fail(FLMR_ERR_UNSUPPORTED, "k=%d outside [1, %d]", k, kMaxK);
   if (n_queries == 0) return FLMR_OK;
+  if (const int code = *reinterpret_cast<volatile int*>(ws->h_status))
+    return fail(FLMR_ERR_KERNEL,
+                "an earlier scan on this workspace tripped the device watchdog (code %d: %s starved); "
+                "the CUDA context is poisoned", code,
+                code == kDevTimeoutProducer ? "TMA producer" : code == kDevTimeoutMma ? "MMA issuer" : "epilogue");
   DeviceGuard guard(c->device);
   if (!guard.ok) return fail(FLMR_ERR_CUDA, "cudaSetDevice(%d) failed", c->device);
 
@@ -504,7 +502,6 @@ int run_search(const flmr_corpus* c, flmr_workspace* ws, const void* d_q, int n_
   p.cand_keys = ws->d_cand_keys;
   p.q_pad = reinterpret_cast<const uint4*>(ws->d_qpad);
   p.status = ws->d_status;
-  p.timeout_ns = 4000000000ull;
   p.lane_mode_max_rbq = 4;   // measured (profiles/r01_debug_mode_probes.log): lane-per-query wins up to 4 row blocks per query
   if (const char* e = getenv("FLMR_LANE_RBQ")) p.lane_mode_max_rbq = atoi(e);
   if (const char* e = getenv("FLMR_DEBUG_MODE")) p.debug_mode = atoi(e);
@@ -526,7 +523,6 @@ int run_search(const flmr_corpus* c, flmr_workspace* ws, const void* d_q, int n_
       }
     }
   }
-  if (const char* e = getenv("FLMR_WATCHDOG_MS")) p.timeout_ns = strtoull(e, nullptr, 10) * 1000000ull;
 
   const int rbq_total = (nq + 31) / 32;
   int rc;
@@ -734,6 +730,15 @@ int flmr_corpus_create(const void* tokens, const int32_t* h_doclens, int64_t n_p
   }
   if ((rc = encode_rows_map(&c->tmap_d, c->d_tokens, static_cast<uint64_t>(n_rows), kTileN)))
     return bail(rc);
+  {  // per-device function attribute, set here (idempotent) rather than at launch time
+    cudaError_t e1 = cudaFuncSetAttribute(flmr_scan_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          ScanSmem::kBytes);
+    cudaError_t e2 = cudaFuncSetAttribute(flmr_scan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          ScanSmem::kBytes);
+    if (e1 != cudaSuccess || e2 != cudaSuccess)
+      return bail(fail(FLMR_ERR_CUDA, "cannot raise the dynamic shared memory limit to %d bytes: %s",
+                       ScanSmem::kBytes, cudaGetErrorString(e1 != cudaSuccess ? e1 : e2)));
+  }
   *out = c;
   return FLMR_OK;
 }

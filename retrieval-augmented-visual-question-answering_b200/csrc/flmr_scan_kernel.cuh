@@ -100,8 +100,7 @@ struct ScanParams {
                                    // 4 = MMA issue never waits for the epilogue (epilogue idle),
                                    // 5 = mode 4 without the per-accumulator commit
                                    // 6 = product + clock64 timestamps of CTA 0's hand-offs -> dbg_ts
-  int* status;
-  uint64_t timeout_ns;
+  int* status;                     // mapped pinned host word: watchdog code of a trapped launch
   long long* dbg_ts;               // [64 accumulators][8] timestamps (debug_mode 6), else null
 };
 
@@ -340,7 +339,7 @@ flmr_scan_kernel(const __grid_constant__ CUtensorMap tmap_d, const ScanParams p)
     for (int t = 0; t < n_tiles; ++t) {
       const int s = t % kDStages;
       const uint32_t ph = (t / kDStages) & 1;
-      mbar_wait(bar_d_empty(s), ph ^ 1u, p.status, kDevTimeoutProducer, p.timeout_ns);
+      mbar_wait(bar_d_empty(s), ph ^ 1u, p.status, kDevTimeoutProducer);
       if (elect_one_sync()) {
         mbar_arrive_expect_tx(bar_d_full(s), kDTileBytes);
         const uint32_t dst = smem_base + S::kOffD + s * kDTileBytes;
@@ -361,12 +360,12 @@ flmr_scan_kernel(const __grid_constant__ CUtensorMap tmap_d, const ScanParams p)
     // descriptors stay in uniform registers.
     const uint32_t iw = static_cast<uint32_t>(warp - kWarpMma);
     constexpr uint32_t idesc = make_idesc_bf16_f32(kTileM, kTileN);
-    mbar_wait(bar_q_full, 0, p.status, kDevTimeoutMma, p.timeout_ns);  // queries are in TMEM
+    mbar_wait(bar_q_full, 0, p.status, kDevTimeoutMma);  // queries are in TMEM
     tc_fence_after_sync();
     for (int t = 0; t < n_tiles; ++t) {
       const int s = t % kDStages;
       const uint32_t ph = (t / kDStages) & 1;
-      mbar_wait(bar_d_full(s), ph, p.status, kDevTimeoutMma, p.timeout_ns);
+      mbar_wait(bar_d_full(s), ph, p.status, kDevTimeoutMma);
       tc_fence_after_sync();
       const uint64_t b_desc0 = make_kmajor_sw128_desc(smem_base + S::kOffD + s * kDTileBytes);
       const uint32_t a_first = static_cast<uint32_t>(t) * n_mtiles;
@@ -375,7 +374,7 @@ flmr_scan_kernel(const __grid_constant__ CUtensorMap tmap_d, const ScanParams p)
         const uint32_t mt = a - a_first;
         const uint32_t as = a & stage_mask, aph = (a >> stage_shift) & 1u;  // TMEM stage / phase
         if (dbg != 4 && dbg != 5) {  // (modes 4/5: never wait for the epilogue)
-          mbar_wait(bar_t_empty(as), aph ^ 1u, p.status, kDevTimeoutMma, p.timeout_ns);
+          mbar_wait(bar_t_empty(as), aph ^ 1u, p.status, kDevTimeoutMma);
           tc_fence_after_sync();
         }
         const uint32_t d_tmem = tmem_base + acc_col0 + as * kTileN;
@@ -449,7 +448,7 @@ flmr_scan_kernel(const __grid_constant__ CUtensorMap tmap_d, const ScanParams p)
       const int buf = t & 1;
       // the reducers must have consumed the partial sums of tile t-2 before this buffer is reused
       mbar_wait(bar_p_empty(buf), ((static_cast<uint32_t>(t) >> 1) & 1u) ^ 1u, p.status,
-                kDevTimeoutEpilogue, p.timeout_ns);
+                kDevTimeoutEpilogue);
       const uint32_t a_first = static_cast<uint32_t>(t) * n_mtiles;
 #pragma unroll 1
       for (uint32_t a = a_first + ((a_first ^ static_cast<uint32_t>(wg)) & 1u); a < a_first + n_mtiles;
@@ -461,10 +460,10 @@ flmr_scan_kernel(const __grid_constant__ CUtensorMap tmap_d, const ScanParams p)
         // it is this very warp, and program order suffices
         if (carry_crosses && t > 0)
           mbar_wait(bar_carry(mt, quad), static_cast<uint32_t>(t - 1) & 1u, p.status,
-                    kDevTimeoutEpilogue, p.timeout_ns);
+                    kDevTimeoutEpilogue);
         float m = carry[mt * kTileM];
         if (quad == 0 && lane == 0) dbg_stamp<kDebug>(p, cta, a, 2);               // epilogue ready to wait
-        mbar_wait(bar_t_full(as), aph, p.status, kDevTimeoutEpilogue, p.timeout_ns);
+        mbar_wait(bar_t_full(as), aph, p.status, kDevTimeoutEpilogue);
         tc_fence_after_sync();
         if (quad == 0 && lane == 0) dbg_stamp<kDebug>(p, cta, a, 3);               // accumulator visible
         if (dbg == 1 || dbg == 3) {  // timing experiment: release unread
@@ -532,8 +531,7 @@ flmr_scan_kernel(const __grid_constant__ CUtensorMap tmap_d, const ScanParams p)
         fpid_next = __ldg(p.tile_first_pid + tile_base + t + 1);
       }
       const int buf = t & 1;
-      mbar_wait(bar_p_full(buf), (static_cast<uint32_t>(t) >> 1) & 1u, p.status, kDevTimeoutEpilogue,
-                p.timeout_ns);
+      mbar_wait(bar_p_full(buf), (static_cast<uint32_t>(t) >> 1) & 1u, p.status, kDevTimeoutEpilogue);
       const int n_slots = __popc(mask);
       const float* lane_part0 = reinterpret_cast<const float*>(smem + S::kOffLanePart);
 #pragma unroll 1

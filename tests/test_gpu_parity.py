@@ -250,5 +250,9 @@ def test_searcher_facade(R, tmp_path):
     s0 = O.maxsim_scores(Q[0:1], D, dl)[0]
     even = np.arange(0, 800, 2)
     assert pids == even[np.argsort(-s0[even], kind="stable")[:5]].tolist()
+    # k beyond the fused top-k capacity (FLMR_MAX_K = 128): all scores from the scan + selection
+    pids, ranks, scores = searcher.dense_search(torch.from_numpy(Q[1:2]), k=300)
+    s1 = O.maxsim_scores(Q[1:2], D, dl)[0]
+    assert pids == np.argsort(-s1, kind="stable")[:300].tolist() and len(ranks) == 300
     with pytest.raises(RuntimeError):
         R.Searcher(index=path, disable_gpu=True)
