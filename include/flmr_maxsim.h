@@ -146,6 +146,16 @@ int flmr_topk_merge(const float* d_in_scores, const int64_t* d_in_pids, int n_li
                     void* stream);
 
 /*
+ * Top-k of dense score rows for k beyond FLMR_MAX_K (Searcher.dense_search accepts any k,
+ * CB/searcher.py:91-132; replaces the `scores.sort(descending=True)[:k]` of IndexScorer.rank):
+ * radix select + order-preserving compaction + bitonic sort, one block per query.
+ *   d_scores fp32 [n_queries, n] (e.g. from flmr_maxsim_scores), k <= 2048, ties -> lower id first;
+ *   outputs as flmr_maxsim_topk (pid = pid_base + column; -inf / -1 fill when n < k).
+ */
+int flmr_topk_select(const float* d_scores, int n_queries, int64_t n, int k, int64_t pid_base,
+                     float* d_out_scores, int64_t* d_out_pids, int device, void* stream);
+
+/*
  * Decode a chunk of a PLAID (ColBERTv2 residual-compressed) index into bf16 token embeddings,
  * so existing reference indexes can be scanned without re-encoding.  Replaces
  * decompress_residuals_cpp (CB/search/decompress_residuals.cpp:80-155), its CUDA twin

@@ -2,9 +2,9 @@
 repository accelerates).  Import name: ``ravqa_b200`` (the directory name carries hyphens)."""
 from . import _cabi  # noqa: F401
 from .corpus import FlatCorpus  # noqa: F401
-from .maxsim import maxsim_scores, maxsim_topk, topk_merge, debug_scores_simt  # noqa: F401
+from .maxsim import maxsim_scores, maxsim_topk, topk_merge, topk_select, debug_scores_simt  # noqa: F401
 
-__all__ = ["FlatCorpus", "maxsim_scores", "maxsim_topk", "topk_merge", "debug_scores_simt"]
+__all__ = ["FlatCorpus", "maxsim_scores", "maxsim_topk", "topk_merge", "topk_select", "debug_scores_simt"]
 from .searcher import Searcher, Ranking  # noqa: F401,E402
 from .sharded import ShardedSearcher, shard_ranges  # noqa: F401,E402
 from .index_io import save_flat_index, load_flat_index  # noqa: F401,E402

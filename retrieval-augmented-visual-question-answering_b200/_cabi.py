@@ -18,6 +18,7 @@ CORPUS_ADOPT = 1
 DIM = 128
 TOKEN_GROUP = 4
 MAX_K = 128
+SELECT_MAX_K = 2048
 
 
 def _header_define(name: str) -> int:
@@ -34,7 +35,7 @@ SYMBOLS = [
     "flmr_last_error", "flmr_abi_version",
     "flmr_corpus_create", "flmr_corpus_destroy", "flmr_corpus_info",
     "flmr_workspace_create", "flmr_workspace_destroy", "flmr_workspace_status",
-    "flmr_maxsim_scores", "flmr_maxsim_topk", "flmr_topk_merge", "flmr_plaid_decode",
+    "flmr_maxsim_scores", "flmr_maxsim_topk", "flmr_topk_merge", "flmr_topk_select", "flmr_plaid_decode",
     "flmr_debug_maxsim_scores_simt", "flmr_debug_build_partition",
     "flmr_launch_count", "flmr_set_profiling", "flmr_scan_kernel_stats",
 ]
@@ -78,6 +79,7 @@ def lib() -> C.CDLL:
     L.flmr_maxsim_scores.argtypes = [vp, vp, vp, i32, i32, u32, vp, vp]
     L.flmr_maxsim_topk.argtypes = [vp, vp, vp, i32, i32, i32, u32, vp, vp, vp]
     L.flmr_topk_merge.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp, i32, vp]
+    L.flmr_topk_select.argtypes = [vp, i32, i64, i32, i64, vp, vp, i32, vp]
     L.flmr_plaid_decode.argtypes = [vp, vp, i64, vp, i64, vp, i32, i32, i32, vp, i32, vp]
     L.flmr_debug_maxsim_scores_simt.argtypes = [vp, vp, i32, i32, u32, vp, vp]
     L.flmr_debug_build_partition.argtypes = [vp, i64, i32, vp, vp, vp, vp, i64, C.POINTER(i64)]

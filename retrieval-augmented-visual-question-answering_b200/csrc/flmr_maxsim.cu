@@ -336,6 +336,129 @@ flmr_merge_kernel(const uint64_t* __restrict__ keys, const float* __restrict__ i
   }
 }
 
+// Top-k selection over a dense score row for k beyond the fused capacity (SURVEY 8a a10:
+// Searcher.dense_search accepts any k).  One 1024-thread block per query:
+//   1. 4-pass MSB radix select (8 bits per pass, 256-bin histogram in shared memory) over the
+//      order-preserving uint32 image of the scores -> key T of the k-th best score, and how many keys
+//      are strictly better;
+//   2. order-preserving compaction: every thread owns a contiguous slice of the row, block-wide
+//      exclusive scans place the keys > T, then as many keys == T (ascending pid) as still fit;
+//   3. bitonic sort of the k survivors by (score desc, pid asc) in shared memory.
+constexpr int kSelectThreads = 1024;
+constexpr int kSelectMaxK = 2048;
+
+__global__ void __launch_bounds__(kSelectThreads)
+flmr_select_kernel(const float* __restrict__ scores, int64_t n, int k, int64_t pid_base,
+                   float* __restrict__ out_scores, int64_t* __restrict__ out_pids) {
+  __shared__ uint32_t hist[256];
+  __shared__ uint32_t s_prefix, s_need, s_gt_total;
+  __shared__ uint32_t scan_gt[kSelectThreads], scan_eq[kSelectThreads];
+  __shared__ uint32_t sel_ord[kSelectMaxK];
+  __shared__ uint32_t sel_pid[kSelectMaxK];
+  const int tid = threadIdx.x;
+  const float* row = scores + static_cast<int64_t>(blockIdx.x) * n;
+  const int kk = static_cast<int>(n < k ? n : k);
+  // ---- 1. radix select of the kk-th largest ordered key ----
+  if (tid == 0) {
+    s_prefix = 0u;
+    s_need = static_cast<uint32_t>(kk);
+  }
+  uint32_t mask_hi = 0u;
+  for (int shift = 24; shift >= 0; shift -= 8) {
+    for (int i = tid; i < 256; i += kSelectThreads) hist[i] = 0u;
+    __syncthreads();
+    const uint32_t prefix = s_prefix;
+    for (int64_t i = tid; i < n; i += kSelectThreads) {
+      const uint32_t key = float_to_ordered(row[i] + 0.0f);
+      if ((key & mask_hi) == prefix) atomicAdd(&hist[(key >> shift) & 0xFFu], 1u);
+    }
+    __syncthreads();
+    if (tid == 0) {
+      uint32_t need = s_need, bin = 255;
+      for (;; --bin) {                       // from the largest digit down
+        if (hist[bin] >= need || bin == 0) break;
+        need -= hist[bin];
+      }
+      s_need = need;                         // still to take inside this bin
+      s_prefix = prefix | (bin << shift);
+    }
+    __syncthreads();
+    mask_hi |= 0xFFu << shift;
+  }
+  const uint32_t T = s_prefix;               // key of the kk-th best; s_need of the keys == T are taken
+  // ---- 2. order-preserving compaction ----
+  const int64_t per = (n + kSelectThreads - 1) / kSelectThreads;
+  const int64_t i0 = static_cast<int64_t>(tid) * per, i1 = (i0 + per < n) ? i0 + per : n;
+  uint32_t c_gt = 0, c_eq = 0;
+  for (int64_t i = i0; i < i1; ++i) {
+    const uint32_t key = float_to_ordered(row[i] + 0.0f);
+    c_gt += key > T;
+    c_eq += key == T;
+  }
+  scan_gt[tid] = c_gt;
+  scan_eq[tid] = c_eq;
+  __syncthreads();
+  for (int off = 1; off < kSelectThreads; off <<= 1) {   // Hillis-Steele inclusive scans
+    const uint32_t a = tid >= off ? scan_gt[tid - off] : 0u, b = tid >= off ? scan_eq[tid - off] : 0u;
+    __syncthreads();
+    scan_gt[tid] += a;
+    scan_eq[tid] += b;
+    __syncthreads();
+  }
+  if (tid == kSelectThreads - 1) s_gt_total = scan_gt[tid];
+  __syncthreads();
+  const uint32_t gt_total = s_gt_total;
+  uint32_t o_gt = scan_gt[tid] - c_gt, o_eq = gt_total + scan_eq[tid] - c_eq;
+  for (int64_t i = i0; i < i1; ++i) {
+    const uint32_t key = float_to_ordered(row[i] + 0.0f);
+    if (key > T) {
+      sel_ord[o_gt] = key;
+      sel_pid[o_gt++] = static_cast<uint32_t>(i);
+    } else if (key == T) {
+      if (o_eq < static_cast<uint32_t>(kk)) {
+        sel_ord[o_eq] = key;
+        sel_pid[o_eq] = static_cast<uint32_t>(i);
+      }
+      ++o_eq;
+    }
+  }
+  // ---- 3. bitonic sort (descending score, ascending pid) over the next power of two ----
+  int m = 1;
+  while (m < kk) m <<= 1;
+  __syncthreads();
+  for (int i = kk + tid; i < m; i += kSelectThreads) {
+    sel_ord[i] = 0u;                         // empty entries sort last
+    sel_pid[i] = 0xFFFFFFFFu;
+  }
+  __syncthreads();
+  auto before = [&](int a, int b) {          // true if entry a must come before entry b
+    return sel_ord[a] > sel_ord[b] || (sel_ord[a] == sel_ord[b] && sel_pid[a] < sel_pid[b]);
+  };
+  for (int size = 2; size <= m; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int i = tid; i < m; i += kSelectThreads) {
+        const int j = i ^ stride;
+        if (j > i) {
+          const bool up = (i & size) == 0;   // ascending position = better entries first
+          if (up ? before(j, i) : before(i, j)) {
+            const uint32_t to = sel_ord[i], tp = sel_pid[i];
+            sel_ord[i] = sel_ord[j];
+            sel_pid[i] = sel_pid[j];
+            sel_ord[j] = to;
+            sel_pid[j] = tp;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  for (int i = tid; i < k; i += kSelectThreads) {
+    const bool ok = i < kk;
+    out_scores[static_cast<int64_t>(blockIdx.x) * k + i] = ok ? ordered_to_float(sel_ord[i]) : -INFINITY;
+    out_pids[static_cast<int64_t>(blockIdx.x) * k + i] = ok ? pid_base + sel_pid[i] : -1;
+  }
+}
+
 }  // namespace
 
 // ---- handles -----------------------------------------------------------------------------------------
@@ -888,6 +1011,22 @@ int flmr_plaid_decode(const int32_t* d_codes, const uint8_t* d_residuals, int64_
   cudaFree(d_bad);
   if (e != cudaSuccess) return fail(FLMR_ERR_CUDA, "plaid decode failed: %s", cudaGetErrorString(e));
   if (bad) return fail(FLMR_ERR_INVALID_ARG, "a centroid code is outside [0, %lld)", (long long)n_centroids);
+  return FLMR_OK;
+}
+
+int flmr_topk_select(const float* d_scores, int n_queries, int64_t n, int k, int64_t pid_base,
+                     float* d_out_scores, int64_t* d_out_pids, int device, void* stream) {
+  if (!d_scores || !d_out_scores || !d_out_pids) return fail(FLMR_ERR_INVALID_ARG, "null pointer");
+  if (n_queries < 0 || n < 1 || k < 1) return fail(FLMR_ERR_INVALID_ARG, "bad shape n_queries=%d n=%lld k=%d", n_queries, (long long)n, k);
+  if (k > kSelectMaxK) return fail(FLMR_ERR_UNSUPPORTED, "k=%d exceeds the selection capacity %d", k, kSelectMaxK);
+  if (n >= (1ll << 32)) return fail(FLMR_ERR_UNSUPPORTED, "rows of 2^32 or more scores are not supported");
+  if (n_queries == 0) return FLMR_OK;
+  DeviceGuard guard(device);
+  if (!guard.ok) return fail(FLMR_ERR_CUDA, "cudaSetDevice(%d) failed", device);
+  flmr_select_kernel<<<n_queries, kSelectThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      d_scores, n, k, pid_base, d_out_scores, d_out_pids);
+  FLMR_CUDA(cudaGetLastError());
+  ++g_launches;
   return FLMR_OK;
 }
 

@@ -83,6 +83,27 @@ def topk_merge(scores: torch.Tensor, pids: torch.Tensor, k_out: int) -> Tuple[to
     return out_s, out_p
 
 
+def topk_select(scores: torch.Tensor, k: int, pid_base: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Top-k of dense score rows ``[B, n]`` on the GPU for k up to 2048 (radix select kernel): the path
+    for k beyond the fused capacity.  Returns (scores [B,k], pids [B,k]) sorted, ties by lower pid."""
+    if scores.dim() != 2 or not scores.is_cuda:
+        raise ValueError("scores must be a CUDA [n_queries, n] tensor")
+    if not 1 <= k <= _cabi.SELECT_MAX_K:
+        raise ValueError("k=%d outside [1, %d]" % (k, _cabi.SELECT_MAX_K))
+    s = scores.detach().to(torch.float32).contiguous()
+    B, n = s.shape
+    out_s = torch.empty((B, k), dtype=torch.float32, device=s.device)
+    out_p = torch.empty((B, k), dtype=torch.int64, device=s.device)
+    if B == 0:
+        return out_s, out_p
+    with torch.cuda.device(s.device):
+        _cabi.check(_cabi.lib().flmr_topk_select(
+            C.c_void_p(s.data_ptr()), B, n, k, int(pid_base), C.c_void_p(out_s.data_ptr()),
+            C.c_void_p(out_p.data_ptr()), int(s.device.index),
+            C.c_void_p(torch.cuda.current_stream(s.device).cuda_stream)))
+    return out_s, out_p
+
+
 def debug_scores_simt(corpus: FlatCorpus, Q: torch.Tensor, relu: bool = False) -> torch.Tensor:
     """Test infrastructure: independent plain-SIMT fp32 kernel (same contract as maxsim_scores)."""
     Qd = _prep_queries(corpus, Q)

@@ -24,7 +24,7 @@ import torch
 from . import _cabi
 from .corpus import FlatCorpus
 from .index_io import load_flat_index
-from .maxsim import maxsim_scores, maxsim_topk
+from .maxsim import maxsim_scores, maxsim_topk, topk_select
 
 
 class Ranking:
@@ -132,8 +132,11 @@ class Searcher:
             if keep is not None:
                 s = s[:, keep]
             kq = min(kk, s.size(1))
-            vals, idx = torch.sort(s, dim=1, descending=True, stable=True)
-            vals, idx = vals[:, :kq], idx[:, :kq]
+            if kq <= _cabi.SELECT_MAX_K:
+                vals, idx = topk_select(s, kq)                       # radix-select kernel
+            else:
+                vals, idx = torch.sort(s, dim=1, descending=True, stable=True)
+                vals, idx = vals[:, :kq], idx[:, :kq]
             pids = (keep[idx] if keep is not None else idx) + self.corpus.pid_base
             outs.append(vals)
             outp.append(pids)

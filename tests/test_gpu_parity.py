@@ -256,3 +256,20 @@ def test_searcher_facade(R, tmp_path):
     assert pids == np.argsort(-s1, kind="stable")[:300].tolist() and len(ranks) == 300
     with pytest.raises(RuntimeError):
         R.Searcher(index=path, disable_gpu=True)
+
+
+def test_topk_select_kernel(R):
+    """flmr_topk_select (k beyond the fused capacity): radix select + ordered compaction + bitonic sort."""
+    rng = np.random.default_rng(5)
+    for n, k in [(50_000, 1000), (4097, 2048), (300, 500), (1, 1), (70_000, 129)]:
+        s = rng.standard_normal((3, n)).astype(np.float32)
+        s[1] = np.round(s[1], 1)                                   # massive ties -> lower pid first
+        if n > 10:
+            s[2, :7] = np.inf
+            s[2, 7:9] = -np.inf
+        vs, ps = R.topk_select(torch.from_numpy(s).cuda(), k, pid_base=10)
+        rs, rp = O.topk(s, k, pid_base=10)
+        assert np.array_equal(ps.cpu().numpy(), rp), (n, k)
+        assert np.array_equal(vs.cpu().numpy(), rs), (n, k)
+    with pytest.raises(ValueError):
+        R.topk_select(torch.zeros(2, 10, device="cuda"), 4096)
