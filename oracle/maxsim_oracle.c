@@ -13,7 +13,7 @@
  * per pthread (segmented_maxsim.cpp:25-28).
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline may call this.  Parity is pinned
- * through tests/golden/*.npz (outputs of the reference itself), see oracle/maxsim_oracle.py.
+ * through the npz fixtures under tests/golden (outputs of the reference itself), see oracle/maxsim_oracle.py.
  */
 #include <math.h>
 #include <pthread.h>
