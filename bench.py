@@ -19,6 +19,7 @@ from __future__ import annotations
 
 import argparse
 import json
+import math
 import os
 import statistics
 import subprocess
@@ -46,6 +47,10 @@ def parse_args():
     ap.add_argument("--k", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU time of the baseline sample")
+    ap.add_argument("--no-plaid-baseline", action="store_true")
+    ap.add_argument("--plaid-passages", type=int, default=50_000,
+                    help="passages in the sample PLAID index of the PLAID CPU-search baseline leg")
+    ap.add_argument("--plaid-ndocs", type=int, default=1024, help="ndocs of the PLAID leg (reference default 1024)")
     return ap.parse_args()
 
 
@@ -130,6 +135,86 @@ def cpu_reference_rate(args, target_seconds, steps=1, warmup=0):
                       "%.2f s per step, linearly extrapolated to the full corpus" %
                       (n_sample, args.passages, args.nq, args.nd, t_step),
             "ms_per_step": t_step * 1e3}
+
+
+def cpu_plaid_rate(args, device, target_seconds=10.0):
+    """queries/sec of the reference's PLAID CPU search (what FLMR_executor.py:778-792 runs under DDP):
+    oracle/plaid_search.py = restated glue + the reference's own compiled kernels (oracle/_ref).
+
+    A PLAID index of the full 1M x 180 corpus is a ~6.5 GB build; the leg is bounded to a clustered sample
+    of `--plaid-passages` passages (index build on `device`, outside the timed region) and says so: PLAID's
+    candidate lists grow with the corpus, so the figure is an UPPER bound of its rate at 1M passages.
+    PLAID returns an approximate ranking; the exhaustive legs return the exact one."""
+    import torch
+    from oracle import plaid_search as P
+    if not P.have_reference_kernels():
+        return {"value": None, "unit": UNIT, "kind": "unavailable", "sample": "oracle/_ref/*.so not built"}
+    try:
+        if os.environ.get("OMP_NUM_THREADS") == "1" or torch.get_num_threads() == 1:
+            torch.set_num_threads(max(1, len(os.sched_getaffinity(0)) // 2))
+    except Exception:
+        pass
+    n, nd, nq, nbits = args.plaid_passages, args.nd, args.nq, 2
+    n_emb = n * nd
+    K = int(2 ** math.floor(math.log2(16 * math.sqrt(n_emb))))   # collection_indexer.py:93
+    dev = torch.device(device)
+    g = torch.Generator(device=dev).manual_seed(1234)
+    t0 = time.perf_counter()
+    # clustered synthetic tokens: topic direction + per-dimension noise 0.06 (token/topic cosine ~0.83,
+    # residual norms in the range real ColBERT indexes show); 256 topics, 3 per passage, so the
+    # candidate list of a query grows linearly with the corpus (~1.2 % of the passages per topic).
+    n_topics = 256
+    topics = torch.nn.functional.normalize(torch.randn(n_topics, 128, generator=g, device=dev), dim=-1)
+    ptop = torch.randint(0, n_topics, (n, 3), generator=g, device=dev)
+    pick = torch.randint(0, 3, (n, nd), generator=g, device=dev)
+    tok_topic = torch.gather(ptop, 1, pick).flatten()
+    D = torch.empty(n_emb, 128, dtype=torch.bfloat16, device=dev)
+    for a in range(0, n_emb, 1 << 20):
+        b = min(n_emb, a + (1 << 20))
+        D[a:b] = torch.nn.functional.normalize(
+            topics[tok_topic[a:b]] + 0.06 * torch.randn(b - a, 128, generator=g, device=dev), dim=-1).bfloat16()
+    doclens = torch.full((n,), nd, dtype=torch.long)
+    sample = D[torch.randperm(n_emb, generator=g, device=dev)[: min(n_emb, 8 * K)]].float()
+    centroids = P.train_centroids(sample.cpu(), K, iters=4, seed=0, device=dev)
+    index = P.PlaidIndex.build(D, doclens, centroids, nbits, heldout=sample[: 1 << 16], device=dev)
+    # queries: Nq noisy tokens of a planted passage (the first query_maxlen=32 select the cells, all Nq score)
+    n_queries = 64
+    targets = torch.randint(0, n, (n_queries,), generator=g, device=dev)
+    rows = torch.randint(0, nd, (n_queries, nq), generator=g, device=dev) + (targets * nd).unsqueeze(1)
+    Q = torch.nn.functional.normalize(D[rows.flatten()].float().view(n_queries, nq, 128)
+                                      + 0.04 * torch.randn(n_queries, nq, 128, generator=g, device=dev), dim=-1)
+    Q = Q.bfloat16().float().cpu()
+    targets = targets.cpu().tolist()
+    del D, sample
+    t_build = time.perf_counter() - t0
+    searcher = P.PlaidSearcher(index)
+    kw = dict(ncells=2, threshold=0.45, ndocs=getattr(args, "plaid_ndocs", 1024), query_maxlen=32)      # colbert/searcher.py:100-103 (k <= 10)
+    n_cand = []
+    for i in range(2):                                                     # warm-up + candidate-count check
+        cand, _ = searcher.retrieve(Q[i:i + 1], kw["ncells"], kw["query_maxlen"])
+        n_cand.append(int(cand.numel()))
+    if min(n_cand) < kw["ndocs"]:
+        return {"value": None, "unit": UNIT, "kind": "unavailable",
+                "sample": "only %d candidates < ndocs=%d on a %d-passage sample: filter_pids.cpp is undefined there"
+                          % (min(n_cand), kw["ndocs"], n)}
+    searcher.rank(Q[0:1], **kw)
+    hits, done, t_total = 0, 0, 0.0
+    for i in range(n_queries):
+        t1 = time.perf_counter()
+        pids, _ = searcher.rank(Q[i:i + 1], **kw)
+        t_total += time.perf_counter() - t1
+        hits += int(targets[i] in pids[: args.k])
+        done += 1
+        if t_total > target_seconds:
+            break
+    return {"value": done / t_total, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "reference",
+            "ms_per_query": 1e3 * t_total / done, "planted_passage_in_top_k": hits / done,
+            "candidates_per_query": n_cand, "index": {"passages": n, "centroids": K, "nbits": nbits,
+                                                      "build_seconds": t_build, "build_device": str(dev)},
+            "sample": "%d queries (Nq=%d, first 32 tokens select cells) through the restated IndexScorer.rank "
+                      "(ncells=2, centroid_score_threshold=0.45, ndocs=%d) over a clustered %d-passage x Nd=%d "
+                      "PLAID index, nbits=2; NOT extrapolated to 1M passages (candidate lists grow with the corpus), "
+                      "approximate ranking" % (done, nq, kw["ndocs"], n, nd)}
 
 
 def run_reference(args):
@@ -400,6 +485,11 @@ def run_ours(args):
                 line["cpu_baseline"] = {kk: base[kk] for kk in ("value", "unit", "cores", "kind", "sample")}
             except Exception as e:  # the baseline must never take the bench line down
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": None, "kind": "error", "sample": repr(e)}
+        if world == 1 and not args.no_cpu_baseline and not args.no_plaid_baseline:
+            try:
+                line["cpu_baseline_plaid"] = cpu_plaid_rate(args, "cuda:%d" % local_rank)
+            except Exception as e:
+                line["cpu_baseline_plaid"] = {"value": None, "unit": UNIT, "kind": "error", "sample": repr(e)}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
