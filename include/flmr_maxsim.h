@@ -171,6 +171,31 @@ int flmr_plaid_decode(const int32_t* d_codes, const uint8_t* d_residuals, int64_
                       const float* d_centroids, int64_t n_centroids, const float* d_bucket_weights,
                       int nbits, int dim, int normalize, void* d_out_bf16, int device, void* stream);
 
+/*
+ * Backward of the all-pairs MaxSim used in training and RAG re-scoring.  The
+ * reference differentiates colbert_score through torch autograd (CB/modeling/colbert.py:235-286,
+ * callers colbert.py:64-113 and src/models/rag/rag_model_blip.py:430-437), keeping the [n, Nd, Nq]
+ * score tensor alive; here nothing is kept by the forward and the winners are recomputed:
+ *
+ * flmr_maxsim_argmax:   d_argmax[b, p, i] = argmax_{j : d_mask[p, j] != 0} <Q[b, i], D[p, j]>
+ *                       (index into the PADDED document, lowest j on ties, -1 if p is fully masked).
+ * flmr_maxsim_backward: given d_grad[b, p] = dLoss/dScore[b, p],
+ *                         d_dq[b, i, :]                  = sum_p grad[b, p] * D[p, argmax[b, p, i], :]
+ *                         d_dd[p, argmax[b, p, i], :]   += grad[b, p] * Q[b, i, :]      (d_dd zeroed first)
+ *                       either output may be NULL.  d_dd is accumulated with fp32 atomics.
+ *   d_q     bf16 [n_queries, nq, FLMR_DIM]        d_docs bf16 [n_docs, nd, FLMR_DIM] (padded, contiguous)
+ *   d_mask  uint8 [n_docs, nd] (any pattern, e.g. the punctuation mask of ColBERT.doc)
+ *   d_argmax int32 [n_queries, n_docs, nq]        d_dq fp32 [n_queries, nq, FLMR_DIM]
+ *   d_dd    fp32 [n_docs, nd, FLMR_DIM]
+ * Asynchronous on `stream`; all pointers are device pointers on `device`.
+ */
+int flmr_maxsim_argmax(const void* d_q, int n_queries, int nq, const void* d_docs,
+                       const uint8_t* d_mask, int n_docs, int nd, int32_t* d_argmax, int device,
+                       void* stream);
+int flmr_maxsim_backward(const void* d_q, int n_queries, int nq, const void* d_docs, int n_docs, int nd,
+                         const int32_t* d_argmax, const float* d_grad, float* d_dq, float* d_dd,
+                         int device, void* stream);
+
 /* Test infrastructure: plain SIMT fp32 MaxSim of every passage (same contract as
  * flmr_maxsim_scores), independent of the tensor-core kernel. */
 int flmr_debug_maxsim_scores_simt(const flmr_corpus_t* corpus, const void* d_q, int n_queries,

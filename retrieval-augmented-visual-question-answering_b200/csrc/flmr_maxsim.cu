@@ -24,6 +24,7 @@
 
 #include "../../include/flmr_maxsim.h"
 #include "flmr_scan_kernel.cuh"
+#include "flmr_train_kernels.cuh"
 
 namespace {
 
@@ -1027,6 +1028,63 @@ int flmr_topk_select(const float* d_scores, int n_queries, int64_t n, int k, int
       d_scores, n, k, pid_base, d_out_scores, d_out_pids);
   FLMR_CUDA(cudaGetLastError());
   ++g_launches;
+  return FLMR_OK;
+}
+
+int flmr_maxsim_argmax(const void* d_q, int n_queries, int nq, const void* d_docs,
+                       const uint8_t* d_mask, int n_docs, int nd, int32_t* d_argmax, int device,
+                       void* stream) {
+  if (!d_q || !d_docs || !d_mask || !d_argmax) return fail(FLMR_ERR_INVALID_ARG, "null pointer");
+  if (n_queries < 0 || n_docs < 0 || nq <= 0 || nd <= 0)
+    return fail(FLMR_ERR_INVALID_ARG, "bad shape n_queries=%d nq=%d n_docs=%d nd=%d", n_queries, nq, n_docs, nd);
+  if (n_queries > 65535 || n_docs > 65535)
+    return fail(FLMR_ERR_UNSUPPORTED, "n_queries / n_docs above 65535 (training-sized batches only)");
+  if (n_queries == 0 || n_docs == 0) return FLMR_OK;
+  DeviceGuard guard(device);
+  if (!guard.ok) return fail(FLMR_ERR_CUDA, "cudaSetDevice(%d) failed", device);
+  dim3 grid(static_cast<unsigned>((nq + kArgTile - 1) / kArgTile), static_cast<unsigned>(n_docs),
+            static_cast<unsigned>(n_queries));
+  flmr_argmax_kernel<<<grid, kArgThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(d_q), static_cast<const __nv_bfloat16*>(d_docs), d_mask, nq, nd,
+      n_docs, d_argmax);
+  FLMR_CUDA(cudaGetLastError());
+  ++g_launches;
+  return FLMR_OK;
+}
+
+int flmr_maxsim_backward(const void* d_q, int n_queries, int nq, const void* d_docs, int n_docs, int nd,
+                         const int32_t* d_argmax, const float* d_grad, float* d_dq, float* d_dd,
+                         int device, void* stream) {
+  if (!d_q || !d_docs || !d_argmax || !d_grad) return fail(FLMR_ERR_INVALID_ARG, "null pointer");
+  if (n_queries < 0 || n_docs < 0 || nq <= 0 || nd <= 0)
+    return fail(FLMR_ERR_INVALID_ARG, "bad shape n_queries=%d nq=%d n_docs=%d nd=%d", n_queries, nq, n_docs, nd);
+  DeviceGuard guard(device);
+  if (!guard.ok) return fail(FLMR_ERR_CUDA, "cudaSetDevice(%d) failed", device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int threads = 256;
+  if (d_dq && n_queries > 0) {
+    const int64_t warps = static_cast<int64_t>(n_queries) * nq;
+    if (n_docs == 0) {
+      FLMR_CUDA(cudaMemsetAsync(d_dq, 0, static_cast<size_t>(warps) * kDim * sizeof(float), st));
+    } else {
+      flmr_bwd_dq_kernel<<<static_cast<unsigned>((warps * 32 + threads - 1) / threads), threads, 0, st>>>(
+          static_cast<const __nv_bfloat16*>(d_docs), d_argmax, d_grad, n_queries, nq, n_docs, nd, d_dq);
+      FLMR_CUDA(cudaGetLastError());
+      ++g_launches;
+    }
+  }
+  if (d_dd && n_docs > 0) {
+    FLMR_CUDA(cudaMemsetAsync(d_dd, 0, static_cast<size_t>(n_docs) * nd * kDim * sizeof(float), st));
+    const int64_t warps = static_cast<int64_t>(n_queries) * n_docs * nq;
+    if (warps > 0) {
+      if ((warps * 32 + threads - 1) / threads > 0x7fffffffll)
+        return fail(FLMR_ERR_UNSUPPORTED, "backward grid too large (%lld warps)", (long long)warps);
+      flmr_bwd_dd_kernel<<<static_cast<unsigned>((warps * 32 + threads - 1) / threads), threads, 0, st>>>(
+          static_cast<const __nv_bfloat16*>(d_q), d_argmax, d_grad, n_queries, nq, n_docs, nd, d_dd);
+      FLMR_CUDA(cudaGetLastError());
+      ++g_launches;
+    }
+  }
   return FLMR_OK;
 }
 

@@ -1,0 +1,164 @@
+// flmr_train_kernels.cuh — backward of the all-pairs MaxSim used by training / RAG re-scoring
+// (SURVEY.md 8f-2).  The reference differentiates colbert_score through torch autograd
+// (third_party/ColBERT/colbert/modeling/colbert.py:235-286: matmul -> masked max -> sum), which keeps
+// the [n, Nd, Nq] score tensor alive for the backward pass.  Here the forward keeps nothing: the
+// backward recomputes, per (query, document) pair, WHICH document token wins each query token
+// (flmr_argmax_kernel, 4 bytes per (b, p, i) instead of Nd*4), then routes the gradient:
+//     dQ[b, i, :]            = sum_p g[b, p] * D[p, arg[b, p, i], :]      (gather,  flmr_bwd_dq_kernel)
+//     dD[p, arg[b, p, i], :] += g[b, p] * Q[b, i, :]                       (scatter, flmr_bwd_dd_kernel)
+// Shapes are training-sized (tens of documents, hundreds of tokens): a register-tiled SIMT fp32
+// contraction over bf16 operands is within a few percent of what these sizes allow, so the kernels
+// stay simple; the corpus-sized forward is the tcgen05 scan kernel.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+namespace flmr {
+
+constexpr int kArgTile = 64;        // query rows and document tokens per shared-memory tile
+constexpr int kArgThreads = 256;    // 16 x 16 threads, 4 x 4 outputs each
+constexpr int kArgStride = 132;     // bf16 per staged row: 264 B = 66 words -> conflict-free column reads
+
+__device__ __forceinline__ void bf16x4_to_float(uint2 v, float* f) {
+  const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&v.x);
+  const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&v.y);
+  const float2 fa = __bfloat1622float2(a), fb = __bfloat1622float2(b);
+  f[0] = fa.x;
+  f[1] = fa.y;
+  f[2] = fb.x;
+  f[3] = fb.y;
+}
+
+// arg[b, p, i] = argmax_{j : mask[p, j]} <Q[b, i, :], D[p, j, :]>   (lowest j on ties; -1 if p has no
+// unmasked token).  grid = (ceil(Nq / 64), n, B), block = 256.
+__global__ void __launch_bounds__(kArgThreads)
+flmr_argmax_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ d,
+                   const uint8_t* __restrict__ mask, int nq, int nd, int n, int32_t* __restrict__ arg) {
+  __shared__ __align__(16) __nv_bfloat16 qs[kArgTile * kArgStride];
+  __shared__ __align__(16) __nv_bfloat16 ds[kArgTile * kArgStride];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int i0 = blockIdx.x * kArgTile, p = blockIdx.y, b = blockIdx.z;
+  const __nv_bfloat16* qb = q + (static_cast<int64_t>(b) * nq + i0) * 128;
+  const __nv_bfloat16* db = d + static_cast<int64_t>(p) * nd * 128;
+  const uint8_t* mp = mask + static_cast<int64_t>(p) * nd;
+
+  // stage the query tile once (rows past Nq read as zero; their results are never stored)
+  for (int t = tid; t < kArgTile * 32; t += kArgThreads) {
+    const int r = t >> 5, c = t & 31;   // 32 uint2 (4 bf16) per row
+    uint2 v = make_uint2(0u, 0u);
+    if (i0 + r < nq) v = *reinterpret_cast<const uint2*>(qb + static_cast<int64_t>(r) * 128 + c * 4);
+    *reinterpret_cast<uint2*>(qs + r * kArgStride + c * 4) = v;
+  }
+  float best[4];
+  int barg[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    best[r] = -INFINITY;
+    barg[r] = -1;
+  }
+  for (int j0 = 0; j0 < nd; j0 += kArgTile) {
+    __syncthreads();   // previous chunk fully consumed (and the query tile visible on the first trip)
+    for (int t = tid; t < kArgTile * 32; t += kArgThreads) {
+      const int r = t >> 5, c = t & 31;
+      uint2 v = make_uint2(0u, 0u);
+      if (j0 + r < nd) v = *reinterpret_cast<const uint2*>(db + static_cast<int64_t>(j0 + r) * 128 + c * 4);
+      *reinterpret_cast<uint2*>(ds + r * kArgStride + c * 4) = v;
+    }
+    __syncthreads();
+    float acc[4][4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
+#pragma unroll 4
+    for (int k = 0; k < 128; k += 4) {
+      float qf[4][4], df[4][4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+        bf16x4_to_float(*reinterpret_cast<const uint2*>(qs + (ty * 4 + r) * kArgStride + k), qf[r]);
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        bf16x4_to_float(*reinterpret_cast<const uint2*>(ds + (tx + 16 * c) * kArgStride + k), df[c]);
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) acc[r][c] = fmaf(qf[r][e], df[c][e], acc[r][c]);
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {       // this thread's columns ascend with c and j0: '>' keeps the first
+      const int j = j0 + tx + 16 * c;
+      if (j < nd && mp[j]) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+          if (acc[r][c] > best[r]) {
+            best[r] = acc[r][c];
+            barg[r] = j;
+          }
+      }
+    }
+  }
+  // combine the 16 column owners of a row (one half-warp); ties -> lower token index
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+#pragma unroll
+    for (int off = 8; off > 0; off >>= 1) {
+      const float ob = __shfl_xor_sync(0xffffffffu, best[r], off);
+      const int oa = __shfl_xor_sync(0xffffffffu, barg[r], off);
+      const bool take = oa >= 0 && (barg[r] < 0 || ob > best[r] || (ob == best[r] && oa < barg[r]));
+      if (take) {
+        best[r] = ob;
+        barg[r] = oa;
+      }
+    }
+    const int i = i0 + ty * 4 + r;
+    if (tx == 0 && i < nq) arg[(static_cast<int64_t>(b) * n + p) * nq + i] = barg[r];
+  }
+}
+
+// dQ[b, i, :] = sum_p g[b, p] * D[p, arg[b, p, i], :].  One warp per (b, i), 4 dims per lane.
+__global__ void flmr_bwd_dq_kernel(const __nv_bfloat16* __restrict__ d, const int32_t* __restrict__ arg,
+                                   const float* __restrict__ g, int B, int nq, int n, int nd,
+                                   float* __restrict__ dq) {
+  const int64_t w = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= static_cast<int64_t>(B) * nq) return;
+  const int b = static_cast<int>(w / nq), i = static_cast<int>(w % nq);
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int p = 0; p < n; ++p) {
+    const int j = arg[(static_cast<int64_t>(b) * n + p) * nq + i];
+    const float gp = g[static_cast<int64_t>(b) * n + p];
+    if (j < 0) continue;
+    float f[4];
+    bf16x4_to_float(*reinterpret_cast<const uint2*>(d + (static_cast<int64_t>(p) * nd + j) * 128 + lane * 4), f);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) acc[e] = fmaf(gp, f[e], acc[e]);
+  }
+  *reinterpret_cast<float4*>(dq + w * 128 + lane * 4) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+}
+
+// dD[p, arg[b, p, i], :] += g[b, p] * Q[b, i, :].  One warp per (b, p, i); fp32 atomics (the order of
+// the additions, hence the last bits of dD, varies from run to run — as torch's index_add_ on CUDA).
+__global__ void flmr_bwd_dd_kernel(const __nv_bfloat16* __restrict__ q, const int32_t* __restrict__ arg,
+                                   const float* __restrict__ g, int B, int nq, int n, int nd,
+                                   float* __restrict__ dd) {
+  const int64_t w = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= static_cast<int64_t>(B) * n * nq) return;
+  const int i = static_cast<int>(w % nq);
+  const int64_t bp = w / nq;
+  const int p = static_cast<int>(bp % n), b = static_cast<int>(bp / n);
+  const int j = arg[w];
+  const float gp = g[bp];
+  if (j < 0 || gp == 0.f) return;
+  float f[4];
+  bf16x4_to_float(*reinterpret_cast<const uint2*>(q + (static_cast<int64_t>(b) * nq + i) * 128 + lane * 4), f);
+  float* dst = dd + (static_cast<int64_t>(p) * nd + j) * 128 + lane * 4;
+#pragma unroll
+  for (int e = 0; e < 4; ++e) atomicAdd(dst + e, gp * f[e]);
+}
+
+}  // namespace flmr

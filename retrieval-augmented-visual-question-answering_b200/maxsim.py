@@ -104,6 +104,52 @@ def topk_select(scores: torch.Tensor, k: int, pid_base: int = 0) -> Tuple[torch.
     return out_s, out_p
 
 
+def _train_operands(Q: torch.Tensor, D_padded: torch.Tensor):
+    if not (Q.is_cuda and D_padded.is_cuda):
+        raise RuntimeError("the scoring path is CUDA-only (no CPU fallback)")
+    if Q.dim() != 3 or D_padded.dim() != 3 or Q.size(2) != _cabi.DIM or D_padded.size(2) != _cabi.DIM:
+        raise ValueError("expected Q [B, Nq, %d] and D [n, Nd, %d]" % (_cabi.DIM, _cabi.DIM))
+    return (Q.detach().to(torch.bfloat16).contiguous(), D_padded.detach().to(torch.bfloat16).contiguous())
+
+
+def maxsim_argmax(Q: torch.Tensor, D_padded: torch.Tensor, D_mask: torch.Tensor) -> torch.Tensor:
+    """``arg[b, p, i]`` = index (into the padded document) of the unmasked token of document ``p`` with
+    the largest inner product with query token ``Q[b, i]``; int32 ``[B, n, Nq]``, -1 for a fully masked
+    document.  What the backward of the all-pairs MaxSim needs instead of the ``[n, Nd, Nq]`` score tensor
+    the reference's autograd keeps (colbert.py:235-286)."""
+    Qb, Db = _train_operands(Q, D_padded)
+    B, nq, n, nd = Qb.size(0), Qb.size(1), Db.size(0), Db.size(1)
+    mask = D_mask.reshape(n, nd).to(device=Qb.device, dtype=torch.uint8).contiguous()
+    arg = torch.empty((B, n, nq), dtype=torch.int32, device=Qb.device)
+    with torch.cuda.device(Qb.device):
+        _cabi.check(_cabi.lib().flmr_maxsim_argmax(
+            C.c_void_p(Qb.data_ptr()), B, nq, C.c_void_p(Db.data_ptr()), C.c_void_p(mask.data_ptr()), n, nd,
+            C.c_void_p(arg.data_ptr()), int(Qb.device.index),
+            C.c_void_p(torch.cuda.current_stream(Qb.device).cuda_stream)))
+    return arg
+
+
+def maxsim_backward(Q: torch.Tensor, D_padded: torch.Tensor, arg: torch.Tensor, grad: torch.Tensor,
+                    need_dq: bool = True, need_dd: bool = True):
+    """Gradients of ``scores[b, p] = sum_i <Q[b, i], D[p, arg[b, p, i]]>`` for upstream ``grad [B, n]``:
+    returns (dQ fp32 ``[B, Nq, d]`` or None, dD fp32 ``[n, Nd, d]`` or None)."""
+    Qb, Db = _train_operands(Q, D_padded)
+    B, nq, n, nd = Qb.size(0), Qb.size(1), Db.size(0), Db.size(1)
+    if arg.shape != (B, n, nq) or arg.dtype != torch.int32 or grad.shape != (B, n):
+        raise ValueError("arg must be int32 [B, n, Nq] and grad [B, n]")
+    g = grad.detach().to(torch.float32).contiguous()
+    a = arg.contiguous()
+    dq = torch.empty((B, nq, _cabi.DIM), dtype=torch.float32, device=Qb.device) if need_dq else None
+    dd = torch.empty((n, nd, _cabi.DIM), dtype=torch.float32, device=Qb.device) if need_dd else None
+    with torch.cuda.device(Qb.device):
+        _cabi.check(_cabi.lib().flmr_maxsim_backward(
+            C.c_void_p(Qb.data_ptr()), B, nq, C.c_void_p(Db.data_ptr()), n, nd, C.c_void_p(a.data_ptr()),
+            C.c_void_p(g.data_ptr()), C.c_void_p(dq.data_ptr() if need_dq else None),
+            C.c_void_p(dd.data_ptr() if need_dd else None), int(Qb.device.index),
+            C.c_void_p(torch.cuda.current_stream(Qb.device).cuda_stream)))
+    return dq, dd
+
+
 def debug_scores_simt(corpus: FlatCorpus, Q: torch.Tensor, relu: bool = False) -> torch.Tensor:
     """Test infrastructure: independent plain-SIMT fp32 kernel (same contract as maxsim_scores)."""
     Qd = _prep_queries(corpus, Q)

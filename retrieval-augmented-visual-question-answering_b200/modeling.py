@@ -12,10 +12,12 @@ aligned ``Q_dup`` form the reference builds with ``repeat_interleave`` is a gath
 and the in-batch-negatives matrix IS that matrix.  The ``[n, Nd, Nq]`` score tensor the reference
 materialises (218 MB per rank at C4) never exists.
 
-Backward (first version): the arg-max token of every (query token, document) pair is recomputed in
-chunks with plain torch ops and the gradients are scattered (``dQ_i += g * D_argmax``,
-``dD_argmax += g * Q_i``); a fused arg-max-saving kernel is round-2 work.
-Inputs are rounded to bf16 for the forward, like the reference's fp16 GPU path (colbert.py:205-206).
+Backward: nothing is saved by the forward except the inputs.  ``flmr_maxsim_argmax`` recomputes which
+document token wins every (query token, document) pair — 4 bytes per pair instead of the Nd scores the
+reference's autograd keeps — and ``flmr_maxsim_backward`` routes the gradient (``dQ_i += g * D_argmax``
+gathered, ``dD_argmax += g * Q_i`` scattered with fp32 atomics).  Both are CUDA kernels behind the C ABI
+(csrc/flmr_train_kernels.cuh).  Inputs are rounded to bf16 for forward and backward, like the reference's
+fp16 GPU path (colbert.py:205-206).
 """
 from __future__ import annotations
 
@@ -24,7 +26,7 @@ from typing import Optional
 import torch
 
 from .corpus import FlatCorpus
-from .maxsim import maxsim_scores
+from .maxsim import maxsim_argmax, maxsim_backward, maxsim_scores
 
 
 def _pack(D_padded: torch.Tensor, D_mask: torch.Tensor):
@@ -34,54 +36,80 @@ def _pack(D_padded: torch.Tensor, D_mask: torch.Tensor):
     return D_padded[mask], doclens, mask
 
 
+def _forward_scores(Q: torch.Tensor, D_padded: torch.Tensor, D_mask: torch.Tensor):
+    """All-pairs scores ``[B, n]`` through ONE launch of the scan kernel over the packed documents."""
+    if not Q.is_cuda:
+        raise RuntimeError("the scoring path is CUDA-only (no CPU fallback)")
+    packed, doclens, mask = _pack(D_padded.detach(), D_mask)
+    if int(doclens.min()) < 1:
+        raise ValueError("a document has no unmasked token: its MaxSim score is undefined "
+                         "(-9999 * Nq on the reference's padded path)")
+    corpus = FlatCorpus(packed.to(torch.bfloat16), doclens.cpu(), device=Q.device, adopt=True)
+    try:
+        scores = maxsim_scores(corpus, Q.detach())
+        torch.cuda.current_stream(Q.device).synchronize()   # corpus buffers die with this scope
+    finally:
+        corpus.close()
+    return scores, mask
+
+
 class _AllPairsMaxSim(torch.autograd.Function):
     """scores[b, p] = sum_i max_{j: mask[p, j]} <Q[b, i], D[p, j]>  for all (b, p)."""
 
     @staticmethod
     def forward(ctx, Q: torch.Tensor, D_padded: torch.Tensor, D_mask: torch.Tensor) -> torch.Tensor:
-        if not Q.is_cuda:
-            raise RuntimeError("the scoring path is CUDA-only (no CPU fallback)")
-        packed, doclens, mask = _pack(D_padded.detach(), D_mask)
-        if int(doclens.min()) < 1:
-            raise ValueError("a document has no unmasked token: its MaxSim score is undefined "
-                             "(-9999 * Nq on the reference's padded path)")
-        corpus = FlatCorpus(packed.to(torch.bfloat16), doclens.cpu(), device=Q.device, adopt=True)
-        try:
-            scores = maxsim_scores(corpus, Q.detach())
-            torch.cuda.current_stream(Q.device).synchronize()   # corpus buffers die with this scope
-        finally:
-            corpus.close()
+        scores, mask = _forward_scores(Q, D_padded, D_mask)
         ctx.save_for_backward(Q, D_padded, mask)
         return scores
 
     @staticmethod
     def backward(ctx, grad: torch.Tensor):
         Q, D_padded, mask = ctx.saved_tensors
-        B, nq, d = Q.shape
-        n, nd, _ = D_padded.shape
-        Qf = Q.detach().to(torch.bfloat16).float()
-        Df = D_padded.detach().to(torch.bfloat16).float()
-        grad = grad.float()
-        dQ = torch.zeros_like(Qf) if ctx.needs_input_grad[0] else None
-        dD = torch.zeros_like(Df) if ctx.needs_input_grad[1] else None
-        chunk = max(1, int((256 << 20) // max(1, B * nq * nd * 4)))      # ~256 MB of scores per chunk
-        for p0 in range(0, n, chunk):
-            p1 = min(n, p0 + chunk)
-            S = torch.einsum("bqd,pkd->bpqk", Qf, Df[p0:p1])              # [B, c, nq, nd]
-            S = S.masked_fill(~mask[p0:p1, None, :].unsqueeze(0), float("-inf"))
-            arg = S.argmax(dim=-1)                                        # [B, c, nq]
-            del S
-            g = grad[:, p0:p1]                                            # [B, c]
-            Dsel = Df[p0:p1]                                              # [c, nd, d]
-            if dQ is not None:
-                gathered = Dsel[torch.arange(p1 - p0, device=arg.device)[None, :, None], arg]   # [B, c, nq, d]
-                dQ += (g[:, :, None, None] * gathered).sum(dim=1)
-            if dD is not None:
-                contrib = g[:, :, None, None] * Qf[:, None, :, :]        # [B, c, nq, d]
-                flat_idx = (torch.arange(p1 - p0, device=arg.device)[None, :, None] * nd + arg).reshape(-1)
-                dD[p0:p1].view(-1, d).index_add_(0, flat_idx, contrib.expand(B, p1 - p0, nq, d).reshape(-1, d))
+        need_dq, need_dd = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        if not (need_dq or need_dd):
+            return None, None, None
+        arg = maxsim_argmax(Q, D_padded, mask)
+        dQ, dD = maxsim_backward(Q, D_padded, arg, grad, need_dq=need_dq, need_dd=need_dd)
         return (dQ.to(Q.dtype) if dQ is not None else None,
                 dD.to(D_padded.dtype) if dD is not None else None, None)
+
+
+class _AlignedMaxSim(torch.autograd.Function):
+    """scores[p] = MaxSim(Q[p], D[p]) for ``Q [n, Nq, d]`` aligned with ``D [n, Nd, d]``.
+
+    Callers build ``Q`` with ``repeat_interleave`` (colbert.py:71, rag_model_blip.py:433,
+    FLMR_executor.py:828): runs of identical queries are scored once against all documents (one scan
+    launch over the unique queries) and the aligned entries are gathered."""
+
+    @staticmethod
+    def forward(ctx, Q: torch.Tensor, D_padded: torch.Tensor, D_mask: torch.Tensor) -> torch.Tensor:
+        Qu, inverse = torch.unique_consecutive(Q.detach(), dim=0, return_inverse=True)
+        S, mask = _forward_scores(Qu, D_padded, D_mask)
+        cols = torch.arange(D_padded.size(0), device=S.device)
+        ctx.save_for_backward(Qu, D_padded, mask, inverse)
+        ctx.q_dtype = Q.dtype
+        return S[inverse, cols]
+
+    @staticmethod
+    def backward(ctx, grad: torch.Tensor):
+        Qu, D_padded, mask, inverse = ctx.saved_tensors
+        need_dq, need_dd = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        if not (need_dq or need_dd):
+            return None, None, None
+        n = D_padded.size(0)
+        cols = torch.arange(n, device=grad.device)
+        arg = maxsim_argmax(Qu, D_padded, mask)                               # [U, n, Nq]
+        dQ = dD = None
+        if need_dd:
+            G = torch.zeros((Qu.size(0), n), dtype=torch.float32, device=grad.device)
+            G[inverse, cols] = grad.float()
+            dD = maxsim_backward(Qu, D_padded, arg, G, need_dq=False, need_dd=True)[1].to(D_padded.dtype)
+        if need_dq:                                                            # row p: grad[p] * D[p, arg[p]]
+            idx = arg[inverse, cols].long().clamp_min(0)                       # [n, Nq]
+            Dsel = D_padded.detach().to(torch.bfloat16).float().gather(
+                1, idx.unsqueeze(-1).expand(-1, -1, D_padded.size(2)))
+            dQ = (grad.float()[:, None, None] * Dsel).to(ctx.q_dtype)
+        return dQ, dD, None
 
 
 def all_pairs_maxsim(Q: torch.Tensor, D_padded: torch.Tensor, D_mask: torch.Tensor) -> torch.Tensor:
@@ -102,20 +130,73 @@ def colbert_score(Q: torch.Tensor, D_padded: torch.Tensor, D_mask: torch.Tensor,
         raise RuntimeError("this colbert_score is the CUDA path; there is no CPU fallback")
     dev = Q.device if Q.is_cuda else torch.device("cuda", torch.cuda.current_device())
     Q, D_padded, D_mask = Q.to(dev), D_padded.to(dev), D_mask.to(dev)
-    S = all_pairs_maxsim(Q, D_padded, D_mask)
     if Q.size(0) == 1:
-        return S[0]
-    return S.diagonal()
+        return all_pairs_maxsim(Q, D_padded, D_mask)[0]
+    return _AlignedMaxSim.apply(Q, D_padded, D_mask)
+
+
+class _GatherCat(torch.autograd.Function):
+    """``cat(all_gather(x))`` along dim 0 whose backward returns every rank's gradient to the owner of the
+    rows (sum over ranks of the owner's slice): the differentiable form of the gather the reference sketches
+    and leaves disabled (colbert.py:68-69, 115-163 — there remote rows are detached, so a document never
+    receives the gradient of another rank's queries)."""
+
+    @staticmethod
+    def forward(ctx, x: torch.Tensor, group):
+        import torch.distributed as dist
+        world = dist.get_world_size(group)
+        ctx.group, ctx.rank, ctx.rows = group, dist.get_rank(group), x.size(0)
+        outs = [torch.empty_like(x) for _ in range(world)]
+        dist.all_gather(outs, x.contiguous(), group=group)
+        return torch.cat(outs, dim=0)
+
+    @staticmethod
+    def backward(ctx, g: torch.Tensor):
+        import torch.distributed as dist
+        g = g.contiguous().clone()
+        dist.all_reduce(g, op=dist.ReduceOp.SUM, group=ctx.group)
+        return g[ctx.rank * ctx.rows:(ctx.rank + 1) * ctx.rows], None
+
+
+def gather_documents(D_padded: torch.Tensor, D_mask: torch.Tensor, group=None):
+    """Every rank's documents (and masks), concatenated in rank order, differentiable w.r.t. the local rows.
+    Ranks may hold different padded lengths; all are padded (masked out) to the longest."""
+    import torch.distributed as dist
+    n, nd = D_padded.size(0), D_padded.size(1)
+    nd_max = torch.tensor([nd], dtype=torch.int64, device=D_padded.device)
+    dist.all_reduce(nd_max, op=dist.ReduceOp.MAX, group=group)
+    pad = int(nd_max.item()) - nd
+    mask = D_mask.reshape(n, nd).to(torch.uint8)
+    if pad:
+        D_padded = torch.nn.functional.pad(D_padded, (0, 0, 0, pad))
+        mask = torch.nn.functional.pad(mask, (0, pad))
+    return _GatherCat.apply(D_padded, group), _GatherCat.apply(mask, group).bool().unsqueeze(-1)
 
 
 def in_batch_negatives_loss(Q: torch.Tensor, D_padded: torch.Tensor, D_mask: torch.Tensor, nway: int,
-                            return_scores: bool = False):
+                            return_scores: bool = False, cross_rank_negatives: bool = False, group=None,
+                            all_pairs_fn=None):
     """compute_ib_loss_new (colbert.py:82-113): ``Q [B, Nq, d]``, ``D [B*nway, Nd, d]`` with the positive
-    of query i at row ``i*nway`` (colbert.py:103-108); cross-entropy over all ``B*nway`` documents."""
+    of query i at row ``i*nway`` (colbert.py:103-108); cross-entropy over all ``B*nway`` documents.
+
+    ``cross_rank_negatives=True`` (needs an initialised process group; every rank the same B and nway):
+    this rank's queries are scored against the documents of ALL ranks — ``[B, world*B*nway]``, the positive
+    of local query i at column ``rank*B*nway + i*nway`` — one all-gather of the document embeddings forward,
+    one all-reduce of their gradient backward.  The mean over ranks of the returned losses is the
+    cross-entropy of the global batch, and its gradient reaches every document from every rank's queries.
+    ``all_pairs_fn`` replaces the CUDA scorer (host-logic tests only)."""
+    score_fn = all_pairs_maxsim if all_pairs_fn is None else all_pairs_fn
     B = Q.size(0)
     assert D_padded.size(0) == B * nway, (D_padded.size(), B, nway)
-    scores = all_pairs_maxsim(Q, D_padded, D_mask)                        # [B, B*nway]
-    labels = torch.arange(B, device=scores.device) * nway
+    first = 0
+    if cross_rank_negatives:
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()):
+            raise RuntimeError("cross_rank_negatives needs an initialised torch.distributed process group")
+        first = dist.get_rank(group) * B * nway
+        D_padded, D_mask = gather_documents(D_padded, D_mask, group)
+    scores = score_fn(Q, D_padded, D_mask)                                # [B, (world*)B*nway]
+    labels = first + torch.arange(B, device=scores.device) * nway
     loss = torch.nn.functional.cross_entropy(scores, labels)
     return (loss, scores) if return_scores else loss
 
@@ -126,8 +207,10 @@ class FLMRModelForRetrieval(torch.nn.Module):
     wrapped PyTorch encoders (out of scope here), ``score`` / ``forward`` route into the CUDA path."""
 
     def __init__(self, query_encoder: Optional[torch.nn.Module] = None,
-                 doc_encoder: Optional[torch.nn.Module] = None, nway: int = 2, use_ib_negatives: bool = True):
+                 doc_encoder: Optional[torch.nn.Module] = None, nway: int = 2, use_ib_negatives: bool = True,
+                 cross_rank_negatives: bool = False):
         super().__init__()
+        self.cross_rank_negatives = cross_rank_negatives
         self.query_encoder = query_encoder
         self.doc_encoder = doc_encoder
         self.nway = nway
@@ -150,8 +233,12 @@ class FLMRModelForRetrieval(torch.nn.Module):
     def forward(self, Q: torch.Tensor, D: torch.Tensor, D_mask: torch.Tensor):
         """ColBERT.forward on pre-computed embeddings (colbert.py:64-80): ``Q [B, Nq, d]``,
         ``D [B*nway, Nd, d]`` -> (scores [B*nway] of the aligned pairs, ib_loss)."""
-        loss, S = in_batch_negatives_loss(Q, D, D_mask, self.nway, return_scores=True)
+        loss, S = in_batch_negatives_loss(Q, D, D_mask, self.nway, return_scores=True,
+                                          cross_rank_negatives=self.cross_rank_negatives)
         B = Q.size(0)
+        first = 0
+        if self.cross_rank_negatives:
+            first = torch.distributed.get_rank() * B * self.nway
         rows = torch.arange(B, device=S.device).repeat_interleave(self.nway)
-        aligned = S[rows, torch.arange(B * self.nway, device=S.device)]
+        aligned = S[rows, first + torch.arange(B * self.nway, device=S.device)]
         return (aligned, loss) if self.use_ib_negatives else aligned
