@@ -178,7 +178,10 @@ int flmr_plaid_decode(const int32_t* d_codes, const uint8_t* d_residuals, int64_
  * score tensor alive; here nothing is kept by the forward and the winners are recomputed:
  *
  * flmr_maxsim_argmax:   d_argmax[b, p, i] = argmax_{j : d_mask[p, j] != 0} <Q[b, i], D[p, j]>
- *                       (index into the PADDED document, lowest j on ties, -1 if p is fully masked).
+ *                       (index into the PADDED document, lowest j on ties, -1 if p is fully masked);
+ *                       d_rowmax (optional, fp32, same shape) receives the maximum itself: summed over i it
+ *                       is score[b, p], so for a training-sized batch this one launch is the forward AND
+ *                       saves what the backward needs (4 B per pair instead of the Nd scores).
  * flmr_maxsim_backward: given d_grad[b, p] = dLoss/dScore[b, p],
  *                         d_dq[b, i, :]                  = sum_p grad[b, p] * D[p, argmax[b, p, i], :]
  *                         d_dd[p, argmax[b, p, i], :]   += grad[b, p] * Q[b, i, :]      (d_dd zeroed first)
@@ -190,8 +193,8 @@ int flmr_plaid_decode(const int32_t* d_codes, const uint8_t* d_residuals, int64_
  * Asynchronous on `stream`; all pointers are device pointers on `device`.
  */
 int flmr_maxsim_argmax(const void* d_q, int n_queries, int nq, const void* d_docs,
-                       const uint8_t* d_mask, int n_docs, int nd, int32_t* d_argmax, int device,
-                       void* stream);
+                       const uint8_t* d_mask, int n_docs, int nd, int32_t* d_argmax, float* d_rowmax,
+                       int device, void* stream);
 int flmr_maxsim_backward(const void* d_q, int n_queries, int nq, const void* d_docs, int n_docs, int nd,
                          const int32_t* d_argmax, const float* d_grad, float* d_dq, float* d_dd,
                          int device, void* stream);

@@ -486,7 +486,8 @@ struct flmr_workspace {
   int max_queries = 0, max_nq = 0;
   __nv_bfloat16* d_qpad = nullptr;     // [kMtMax*128, 128] staged (zero-padded) queries of one pass
   uint64_t* d_cand_keys = nullptr;     // [n_ctas][kNqMax][kMaxK]
-  float* d_acc = nullptr;              // [n_passages] lazily allocated (row-sliced queries)
+  float* d_acc = nullptr;              // [group][n_passages] lazily allocated (row-sliced queries)
+  int64_t acc_capacity = 0;            // floats allocated at d_acc
   int* h_status = nullptr;             // pinned + mapped: readable by the host even after a device trap
   int* d_status = nullptr;             // device alias of h_status
 };
@@ -670,31 +671,53 @@ int run_search(const flmr_corpus* c, flmr_workspace* ws, const void* d_q, int n_
         return rc;
     }
   } else {
-    // one query at a time, its rows sliced over several corpus passes; partial scores go through HBM
+    // queries longer than one pass holds: rows sliced over several corpus passes, partial scores carried
+    // through HBM (acc_in / acc_out).  Full slices take one pass per query; the TAIL slices of up to
+    // `group` queries share one pass (Nq = 832: 3 queries = 3 full passes + 1 tail pass instead of 6).
     const int rows_per_slice = kRbMax * 32;
     const int n_slices = (nq + rows_per_slice - 1) / rows_per_slice;
-    if (!d_all_scores && !ws->d_acc)
+    const int tail_row0 = (n_slices - 1) * rows_per_slice;
+    const int tail_rows = nq - tail_row0;
+    const int tail_rbq = (tail_rows + 31) / 32;
+    const int group = std::max(1, std::min({kNqMax, kRbMax / tail_rbq, n_queries}));
+    if (!d_all_scores && ws->acc_capacity < static_cast<int64_t>(group) * c->n_passages) {
+      if (ws->d_acc) cudaFree(ws->d_acc);
+      ws->d_acc = nullptr;
+      ws->acc_capacity = 0;
       FLMR_CUDA(cudaMalloc(reinterpret_cast<void**>(&ws->d_acc),
-                           static_cast<size_t>(std::max<int64_t>(c->n_passages, 1)) * sizeof(float)));
-    for (int b = 0; b < n_queries; ++b) {
-      float* acc = d_all_scores ? d_all_scores + static_cast<int64_t>(b) * c->n_passages : ws->d_acc;
-      for (int s = 0; s < n_slices; ++s) {
-        const int row0 = s * rows_per_slice;
-        const int rows = std::min(rows_per_slice, nq - row0);
-        const int rbq = (rows + 31) / 32;
-        const int n_mtiles = (rbq * 32 + kTileM - 1) / kTileM;
-        const bool last = (s == n_slices - 1);
-        if ((rc = stage_queries(ws, d_q, b, 1, nq, row0, rows, rbq, n_mtiles, st))) return rc;
-        p.n_mtiles = n_mtiles;
-        p.nq_pass = 1;
-        p.rbq = rbq;
-        p.acc_in = (s == 0) ? nullptr : acc;
-        p.acc_out = (last && !d_all_scores) ? nullptr : acc;
-        p.k = last ? k : 0;
-        if ((rc = launch_scan(c, ws, p, st))) return rc;
+                           static_cast<size_t>(group) * c->n_passages * sizeof(float)));
+      ws->acc_capacity = static_cast<int64_t>(group) * c->n_passages;
+    }
+    for (int b0 = 0; b0 < n_queries; b0 += group) {
+      const int g = std::min(group, n_queries - b0);
+      float* acc = d_all_scores ? d_all_scores + static_cast<int64_t>(b0) * c->n_passages : ws->d_acc;
+      for (int b = 0; b < g; ++b) {                         // full slices, one query per pass
+        float* acc_b = acc + static_cast<int64_t>(b) * c->n_passages;
+        for (int s = 0; s + 1 < n_slices; ++s) {
+          if ((rc = stage_queries(ws, d_q, b0 + b, 1, nq, s * rows_per_slice, rows_per_slice, kRbMax,
+                                  kRbMax * 32 / kTileM, st)))
+            return rc;
+          p.n_mtiles = kRbMax * 32 / kTileM;
+          p.nq_pass = 1;
+          p.rbq = kRbMax;
+          p.acc_in = (s == 0) ? nullptr : acc_b;
+          p.acc_out = acc_b;
+          p.k = 0;
+          if ((rc = launch_scan(c, ws, p, st))) return rc;
+        }
       }
-      if (k > 0 && (rc = launch_merge_keys(c, ws, 1, k, d_topk_scores + static_cast<int64_t>(b) * k,
-                                           d_topk_pids + static_cast<int64_t>(b) * k, st)))
+      // tail slices of the g queries together
+      const int n_mtiles = (g * tail_rbq * 32 + kTileM - 1) / kTileM;
+      if ((rc = stage_queries(ws, d_q, b0, g, nq, tail_row0, tail_rows, tail_rbq, n_mtiles, st))) return rc;
+      p.n_mtiles = n_mtiles;
+      p.nq_pass = g;
+      p.rbq = tail_rbq;
+      p.acc_in = acc;
+      p.acc_out = d_all_scores ? acc : nullptr;
+      p.k = k;
+      if ((rc = launch_scan(c, ws, p, st))) return rc;
+      if (k > 0 && (rc = launch_merge_keys(c, ws, g, k, d_topk_scores + static_cast<int64_t>(b0) * k,
+                                           d_topk_pids + static_cast<int64_t>(b0) * k, st)))
         return rc;
     }
   }
@@ -1032,8 +1055,8 @@ int flmr_topk_select(const float* d_scores, int n_queries, int64_t n, int k, int
 }
 
 int flmr_maxsim_argmax(const void* d_q, int n_queries, int nq, const void* d_docs,
-                       const uint8_t* d_mask, int n_docs, int nd, int32_t* d_argmax, int device,
-                       void* stream) {
+                       const uint8_t* d_mask, int n_docs, int nd, int32_t* d_argmax, float* d_rowmax,
+                       int device, void* stream) {
   if (!d_q || !d_docs || !d_mask || !d_argmax) return fail(FLMR_ERR_INVALID_ARG, "null pointer");
   if (n_queries < 0 || n_docs < 0 || nq <= 0 || nd <= 0)
     return fail(FLMR_ERR_INVALID_ARG, "bad shape n_queries=%d nq=%d n_docs=%d nd=%d", n_queries, nq, n_docs, nd);
@@ -1046,7 +1069,7 @@ int flmr_maxsim_argmax(const void* d_q, int n_queries, int nq, const void* d_doc
             static_cast<unsigned>(n_queries));
   flmr_argmax_kernel<<<grid, kArgThreads, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(d_q), static_cast<const __nv_bfloat16*>(d_docs), d_mask, nq, nd,
-      n_docs, d_argmax);
+      n_docs, d_argmax, d_rowmax);
   FLMR_CUDA(cudaGetLastError());
   ++g_launches;
   return FLMR_OK;

@@ -32,10 +32,12 @@ __device__ __forceinline__ void bf16x4_to_float(uint2 v, float* f) {
 }
 
 // arg[b, p, i] = argmax_{j : mask[p, j]} <Q[b, i, :], D[p, j, :]>   (lowest j on ties; -1 if p has no
-// unmasked token).  grid = (ceil(Nq / 64), n, B), block = 256.
+// unmasked token); rowmax[b, p, i] = that maximum (optional: summed over i it is the MaxSim score, which
+// makes this kernel the whole forward of a training-sized batch).  grid = (ceil(Nq / 64), n, B), block = 256.
 __global__ void __launch_bounds__(kArgThreads)
 flmr_argmax_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ d,
-                   const uint8_t* __restrict__ mask, int nq, int nd, int n, int32_t* __restrict__ arg) {
+                   const uint8_t* __restrict__ mask, int nq, int nd, int n, int32_t* __restrict__ arg,
+                   float* __restrict__ rowmax) {
   __shared__ __align__(16) __nv_bfloat16 qs[kArgTile * kArgStride];
   __shared__ __align__(16) __nv_bfloat16 ds[kArgTile * kArgStride];
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
@@ -115,7 +117,11 @@ flmr_argmax_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __r
       }
     }
     const int i = i0 + ty * 4 + r;
-    if (tx == 0 && i < nq) arg[(static_cast<int64_t>(b) * n + p) * nq + i] = barg[r];
+    if (tx == 0 && i < nq) {
+      const int64_t o = (static_cast<int64_t>(b) * n + p) * nq + i;
+      arg[o] = barg[r];
+      if (rowmax) rowmax[o] = best[r];
+    }
   }
 }
 

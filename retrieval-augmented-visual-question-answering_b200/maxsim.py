@@ -112,21 +112,23 @@ def _train_operands(Q: torch.Tensor, D_padded: torch.Tensor):
     return (Q.detach().to(torch.bfloat16).contiguous(), D_padded.detach().to(torch.bfloat16).contiguous())
 
 
-def maxsim_argmax(Q: torch.Tensor, D_padded: torch.Tensor, D_mask: torch.Tensor) -> torch.Tensor:
+def maxsim_argmax(Q: torch.Tensor, D_padded: torch.Tensor, D_mask: torch.Tensor, return_rowmax: bool = False):
     """``arg[b, p, i]`` = index (into the padded document) of the unmasked token of document ``p`` with
     the largest inner product with query token ``Q[b, i]``; int32 ``[B, n, Nq]``, -1 for a fully masked
     document.  What the backward of the all-pairs MaxSim needs instead of the ``[n, Nd, Nq]`` score tensor
-    the reference's autograd keeps (colbert.py:235-286)."""
+    the reference's autograd keeps (colbert.py:235-286).  ``return_rowmax=True`` also returns the maxima
+    themselves (fp32, same shape): ``rowmax.sum(-1)`` is the ``[B, n]`` score matrix."""
     Qb, Db = _train_operands(Q, D_padded)
     B, nq, n, nd = Qb.size(0), Qb.size(1), Db.size(0), Db.size(1)
     mask = D_mask.reshape(n, nd).to(device=Qb.device, dtype=torch.uint8).contiguous()
     arg = torch.empty((B, n, nq), dtype=torch.int32, device=Qb.device)
+    rowmax = torch.empty((B, n, nq), dtype=torch.float32, device=Qb.device) if return_rowmax else None
     with torch.cuda.device(Qb.device):
         _cabi.check(_cabi.lib().flmr_maxsim_argmax(
             C.c_void_p(Qb.data_ptr()), B, nq, C.c_void_p(Db.data_ptr()), C.c_void_p(mask.data_ptr()), n, nd,
-            C.c_void_p(arg.data_ptr()), int(Qb.device.index),
-            C.c_void_p(torch.cuda.current_stream(Qb.device).cuda_stream)))
-    return arg
+            C.c_void_p(arg.data_ptr()), C.c_void_p(rowmax.data_ptr() if return_rowmax else None),
+            int(Qb.device.index), C.c_void_p(torch.cuda.current_stream(Qb.device).cuda_stream)))
+    return (arg, rowmax) if return_rowmax else arg
 
 
 def maxsim_backward(Q: torch.Tensor, D_padded: torch.Tensor, arg: torch.Tensor, grad: torch.Tensor,

@@ -6,15 +6,16 @@
                                                 src/executors/FLMR_executor.py:828-833 exhaustive eval)
     compute_ib_loss_new (in-batch negatives)    colbert.py:82-113
 
-The forward is ONE launch of the fused scan kernel: the ``n`` padded documents are packed into a
-temporary FlatCorpus and every query is scored against every document (all pairs ``[B, n]``) — the
-aligned ``Q_dup`` form the reference builds with ``repeat_interleave`` is a gather of that matrix,
-and the in-batch-negatives matrix IS that matrix.  The ``[n, Nd, Nq]`` score tensor the reference
-materialises (218 MB per rank at C4) never exists.
+Forward, training-sized batches (the usual case here): ONE launch of ``flmr_maxsim_argmax`` computes, for
+every (query token, document) pair, the winning document token and its inner product — the row maxima
+summed over query tokens are the all-pairs scores ``[B, n]`` (the aligned ``Q_dup`` form the reference
+builds with ``repeat_interleave`` is a gather of that matrix, the in-batch-negatives matrix IS that
+matrix), and the winners (4 bytes per pair) are what the backward needs.  Large inputs (exhaustive
+evaluation through ``score``): the ``n`` padded documents are packed into a temporary FlatCorpus and
+scored by one launch of the tcgen05 scan kernel; the backward then recomputes the winners.  Either way the
+``[n, Nd, Nq]`` score tensor the reference materialises (218 MB per rank at C4) never exists.
 
-Backward: nothing is saved by the forward except the inputs.  ``flmr_maxsim_argmax`` recomputes which
-document token wins every (query token, document) pair — 4 bytes per pair instead of the Nd scores the
-reference's autograd keeps — and ``flmr_maxsim_backward`` routes the gradient (``dQ_i += g * D_argmax``
+Backward: ``flmr_maxsim_backward`` routes the gradient through the winners (``dQ_i += g * D_argmax``
 gathered, ``dD_argmax += g * Q_i`` scattered with fp32 atomics).  Both are CUDA kernels behind the C ABI
 (csrc/flmr_train_kernels.cuh).  Inputs are rounded to bf16 for forward and backward, like the reference's
 fp16 GPU path (colbert.py:205-206).
@@ -29,28 +30,33 @@ from .corpus import FlatCorpus
 from .maxsim import maxsim_argmax, maxsim_backward, maxsim_scores
 
 
-def _pack(D_padded: torch.Tensor, D_mask: torch.Tensor):
-    n, nd, d = D_padded.shape
-    mask = D_mask.reshape(n, nd).bool()
-    doclens = mask.sum(dim=1)
-    return D_padded[mask], doclens, mask
+# Below this many multiply-accumulates the whole forward is ONE launch of the arg-max kernel (scores =
+# row maxima summed), which also saves the winners for the backward; above it the tcgen05 scan kernel over
+# a temporary packed corpus wins despite its per-call setup (allocation, partition build, TMA descriptor:
+# ~2 ms measured, profiles/r01_train_step_probe.md) and the backward recomputes the winners.
+_FUSED_SMALL_MAX_MACS = 3e10
 
 
 def _forward_scores(Q: torch.Tensor, D_padded: torch.Tensor, D_mask: torch.Tensor):
-    """All-pairs scores ``[B, n]`` through ONE launch of the scan kernel over the packed documents."""
-    if not Q.is_cuda:
+    """All-pairs scores ``[B, n]``; returns (scores, bool mask [n, Nd], saved arg-max or None)."""
+    if not (Q.is_cuda and D_padded.is_cuda):
         raise RuntimeError("the scoring path is CUDA-only (no CPU fallback)")
-    packed, doclens, mask = _pack(D_padded.detach(), D_mask)
-    if int(doclens.min()) < 1:
+    n, nd = D_padded.size(0), D_padded.size(1)
+    mask = D_mask.reshape(n, nd).bool()
+    if not bool(mask.any(dim=1).all()):
         raise ValueError("a document has no unmasked token: its MaxSim score is undefined "
                          "(-9999 * Nq on the reference's padded path)")
-    corpus = FlatCorpus(packed.to(torch.bfloat16), doclens.cpu(), device=Q.device, adopt=True)
+    if float(Q.size(0)) * n * Q.size(1) * nd * Q.size(2) <= _FUSED_SMALL_MAX_MACS:
+        arg, rowmax = maxsim_argmax(Q, D_padded, mask, return_rowmax=True)
+        return rowmax.sum(dim=-1), mask, arg
+    packed = D_padded.detach()[mask]
+    corpus = FlatCorpus(packed.to(torch.bfloat16), mask.sum(dim=1).cpu(), device=Q.device, adopt=True)
     try:
         scores = maxsim_scores(corpus, Q.detach())
         torch.cuda.current_stream(Q.device).synchronize()   # corpus buffers die with this scope
     finally:
         corpus.close()
-    return scores, mask
+    return scores, mask, None
 
 
 class _AllPairsMaxSim(torch.autograd.Function):
@@ -58,17 +64,18 @@ class _AllPairsMaxSim(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, Q: torch.Tensor, D_padded: torch.Tensor, D_mask: torch.Tensor) -> torch.Tensor:
-        scores, mask = _forward_scores(Q, D_padded, D_mask)
-        ctx.save_for_backward(Q, D_padded, mask)
+        scores, mask, arg = _forward_scores(Q, D_padded, D_mask)
+        ctx.has_arg = arg is not None
+        ctx.save_for_backward(Q, D_padded, mask, *([arg] if ctx.has_arg else []))
         return scores
 
     @staticmethod
     def backward(ctx, grad: torch.Tensor):
-        Q, D_padded, mask = ctx.saved_tensors
+        Q, D_padded, mask = ctx.saved_tensors[:3]
         need_dq, need_dd = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         if not (need_dq or need_dd):
             return None, None, None
-        arg = maxsim_argmax(Q, D_padded, mask)
+        arg = ctx.saved_tensors[3] if ctx.has_arg else maxsim_argmax(Q, D_padded, mask)
         dQ, dD = maxsim_backward(Q, D_padded, arg, grad, need_dq=need_dq, need_dd=need_dd)
         return (dQ.to(Q.dtype) if dQ is not None else None,
                 dD.to(D_padded.dtype) if dD is not None else None, None)
@@ -84,21 +91,22 @@ class _AlignedMaxSim(torch.autograd.Function):
     @staticmethod
     def forward(ctx, Q: torch.Tensor, D_padded: torch.Tensor, D_mask: torch.Tensor) -> torch.Tensor:
         Qu, inverse = torch.unique_consecutive(Q.detach(), dim=0, return_inverse=True)
-        S, mask = _forward_scores(Qu, D_padded, D_mask)
+        S, mask, arg = _forward_scores(Qu, D_padded, D_mask)
         cols = torch.arange(D_padded.size(0), device=S.device)
-        ctx.save_for_backward(Qu, D_padded, mask, inverse)
+        ctx.has_arg = arg is not None
+        ctx.save_for_backward(Qu, D_padded, mask, inverse, *([arg] if ctx.has_arg else []))
         ctx.q_dtype = Q.dtype
         return S[inverse, cols]
 
     @staticmethod
     def backward(ctx, grad: torch.Tensor):
-        Qu, D_padded, mask, inverse = ctx.saved_tensors
+        Qu, D_padded, mask, inverse = ctx.saved_tensors[:4]
         need_dq, need_dd = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         if not (need_dq or need_dd):
             return None, None, None
         n = D_padded.size(0)
         cols = torch.arange(n, device=grad.device)
-        arg = maxsim_argmax(Qu, D_padded, mask)                               # [U, n, Nq]
+        arg = ctx.saved_tensors[4] if ctx.has_arg else maxsim_argmax(Qu, D_padded, mask)   # [U, n, Nq]
         dQ = dD = None
         if need_dd:
             G = torch.zeros((Qu.size(0), n), dtype=torch.float32, device=grad.device)

@@ -82,6 +82,9 @@ def test_config_c1_16q_1k_passages(R):
     (900, 200, 3, 96, 100, True, False, 4),      # several queries per pass, k = 100
     (600, 150, 2, 832, 20, True, False, 5),      # FLMR full query (512 text + 320 vision): row slices
     (400, 90, 1, 400, 128, True, True, 6),       # 2 slices, k = FLMR_MAX_K, relu
+    (500, 120, 7, 832, 5, True, False, 15),      # 7 long queries: tail slices share passes in groups of 3 (3+3+1)
+    (300, 60, 3, 1500, 9, True, True, 16),       # 3 slices (640+640+220): tail groups of 2, relu
+    (200, 50, 2, 1280, 4, True, False, 17),      # tail slice is itself a full pass (group of 1)
     (257, 33, 13, 45, 3, True, False, 7),        # nq not a multiple of 32, 13 queries (2 passes)
     (50, 700, 2, 64, 5, True, False, 8),         # passages longer than several 128-token tiles
     (5000, 3, 2, 32, 10, True, False, 9),        # tiny passages: up to 32 passage ends per tile

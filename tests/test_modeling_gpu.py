@@ -131,3 +131,22 @@ def test_aligned_score_with_repeat_interleaved_queries():
     (sr * w).sum().backward()
     np.testing.assert_allclose(Qg.grad.cpu().numpy(), Qr.grad.cpu().numpy(), rtol=1e-4, atol=1e-5)
     np.testing.assert_allclose(Dg.grad.cpu().numpy(), Dr.grad.cpu().numpy(), rtol=1e-4, atol=1e-5)
+
+
+def test_fused_small_forward_and_scan_kernel_forward_agree(monkeypatch):
+    """Training-sized batches take the one-launch arg-max forward, large ones the tcgen05 scan kernel over a
+    packed temporary corpus: same scores (fp32 accumulation of the same bf16 products) and same gradients."""
+    import ravqa_b200 as R
+    from ravqa_b200 import modeling
+    Q, D, mask = _inputs(5, 96, 9, 77, seed=6)
+    outs = []
+    for limit in (modeling._FUSED_SMALL_MAX_MACS, 0.0):
+        monkeypatch.setattr(modeling, "_FUSED_SMALL_MAX_MACS", limit)
+        Qg, Dg = Q.clone().requires_grad_(True), D.clone().requires_grad_(True)
+        S = R.all_pairs_maxsim(Qg, Dg, mask.unsqueeze(-1))
+        (S * torch.linspace(-1, 1, S.numel(), device="cuda").view_as(S)).sum().backward()
+        outs.append((S.detach(), Qg.grad, Dg.grad))
+    np.testing.assert_allclose(outs[0][0].cpu().numpy(), outs[1][0].cpu().numpy(), rtol=2e-6, atol=2e-6)
+    np.testing.assert_allclose(outs[0][1].cpu().numpy(), outs[1][1].cpu().numpy(), rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(outs[0][2].cpu().numpy(), outs[1][2].cpu().numpy(), rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(outs[0][0].cpu().numpy(), _ref_all_pairs(Q, D, mask).cpu().numpy(), rtol=2e-5)
