@@ -653,7 +653,11 @@ int run_search(const flmr_corpus* c, flmr_workspace* ws, const void* d_q, int n_
   int rc;
   if (rbq_total <= kRbMax) {
     // whole queries resident: as many queries per corpus pass as fit kRbMax 32-row blocks
-    const int qpp = std::min(kNqMax, kRbMax / rbq_total);
+    // ... spread evenly over the passes that takes (64 queries of one row block: 4 passes of 16 rather
+    // than 20+20+20+4, whose last pass would be HBM-bound while the others are tensor-bound)
+    const int qpp_max = std::min(kNqMax, kRbMax / rbq_total);
+    const int n_passes = (n_queries + qpp_max - 1) / qpp_max;
+    const int qpp = (n_queries + n_passes - 1) / n_passes;
     for (int b0 = 0; b0 < n_queries; b0 += qpp) {
       const int nqp = std::min(qpp, n_queries - b0);
       const int n_mtiles = (nqp * rbq_total * 32 + kTileM - 1) / kTileM;
