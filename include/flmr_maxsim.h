@@ -172,6 +172,19 @@ int flmr_plaid_decode(const int32_t* d_codes, const uint8_t* d_residuals, int64_
                       int nbits, int dim, int normalize, void* d_out_bf16, int device, void* stream);
 
 /*
+ * Gather retrieved passages out of the resident corpus into a padded batch — the operand of the RAG
+ * re-score (src/models/rag/rag_model_blip.py:414-435 looks the embeddings up in a host dictionary, stacks
+ * them and copies them to the device for every query; here they never leave HBM).
+ *   d_pids   int64 [n_pids] GLOBAL passage ids (pid_base-relative ids are derived inside); ids outside
+ *            this shard (e.g. the -1 fill of a short result list) produce an all-masked, zero row.
+ *   d_out    bf16  [n_pids, nd_max, FLMR_DIM]  tokens, zero-padded; passages longer than nd_max are cut
+ *   d_mask   uint8 [n_pids, nd_max]            1 for real tokens (may be NULL)
+ * Asynchronous on `stream`.
+ */
+int flmr_corpus_gather(const flmr_corpus_t* corpus, const int64_t* d_pids, int64_t n_pids, int nd_max,
+                       void* d_out_bf16, uint8_t* d_mask, void* stream);
+
+/*
  * Backward of the all-pairs MaxSim used in training and RAG re-scoring.  The
  * reference differentiates colbert_score through torch autograd (CB/modeling/colbert.py:235-286,
  * callers colbert.py:64-113 and src/models/rag/rag_model_blip.py:430-437), keeping the [n, Nd, Nq]

@@ -36,7 +36,7 @@ SYMBOLS = [
     "flmr_corpus_create", "flmr_corpus_destroy", "flmr_corpus_info",
     "flmr_workspace_create", "flmr_workspace_destroy", "flmr_workspace_status",
     "flmr_maxsim_scores", "flmr_maxsim_topk", "flmr_topk_merge", "flmr_topk_select", "flmr_plaid_decode",
-    "flmr_maxsim_argmax", "flmr_maxsim_backward",
+    "flmr_maxsim_argmax", "flmr_maxsim_backward", "flmr_corpus_gather",
     "flmr_debug_maxsim_scores_simt", "flmr_debug_build_partition",
     "flmr_launch_count", "flmr_set_profiling", "flmr_scan_kernel_stats",
 ]
@@ -82,6 +82,7 @@ def lib() -> C.CDLL:
     L.flmr_topk_merge.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp, i32, vp]
     L.flmr_topk_select.argtypes = [vp, i32, i64, i32, i64, vp, vp, i32, vp]
     L.flmr_plaid_decode.argtypes = [vp, vp, i64, vp, i64, vp, i32, i32, i32, vp, i32, vp]
+    L.flmr_corpus_gather.argtypes = [vp, vp, i64, i32, vp, vp, vp]
     L.flmr_maxsim_argmax.argtypes = [vp, i32, i32, vp, vp, i32, i32, vp, vp, i32, vp]
     L.flmr_maxsim_backward.argtypes = [vp, i32, i32, vp, i32, i32, vp, vp, vp, vp, i32, vp]
     L.flmr_debug_maxsim_scores_simt.argtypes = [vp, vp, i32, i32, u32, vp, vp]

@@ -127,6 +127,24 @@ class FlatCorpus:
             self._ws = ws
         return self._ws
 
+    def gather_padded(self, pids: torch.Tensor, nd_max: Optional[int] = None):
+        """Retrieved passages as a padded batch, straight out of HBM: ``pids`` (any shape, global ids) ->
+        (tokens bf16 ``[*pids.shape, nd_max, 128]``, mask bool ``[*pids.shape, nd_max, 1]``).  ``nd_max``
+        defaults to the longest requested passage.  Ids outside this shard give an all-masked zero row.
+        Replaces the host-dictionary lookup + stack + H2D of rag_model_blip.py:414-425."""
+        shape = tuple(pids.shape)
+        flat = pids.detach().reshape(-1).to(device=self.device, dtype=torch.int64).contiguous()
+        if nd_max is None:
+            local = (flat - self.pid_base).clamp(0, self.n_passages - 1).cpu().numpy()
+            nd_max = int(self.doclens[local].max()) if flat.numel() else 1
+        out = torch.empty((flat.numel(), nd_max, _cabi.DIM), dtype=torch.bfloat16, device=self.device)
+        mask = torch.empty((flat.numel(), nd_max), dtype=torch.uint8, device=self.device)
+        with torch.cuda.device(self.device):
+            _cabi.check(_cabi.lib().flmr_corpus_gather(
+                self.handle, C.c_void_p(flat.data_ptr()), flat.numel(), int(nd_max), C.c_void_p(out.data_ptr()),
+                C.c_void_p(mask.data_ptr()), C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)))
+        return out.view(*shape, nd_max, _cabi.DIM), mask.bool().view(*shape, nd_max, 1)
+
     def close(self) -> None:
         L = _cabi.lib()
         if self._ws is not None:

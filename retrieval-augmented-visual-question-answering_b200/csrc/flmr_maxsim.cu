@@ -1058,6 +1058,24 @@ int flmr_topk_select(const float* d_scores, int n_queries, int64_t n, int k, int
   return FLMR_OK;
 }
 
+int flmr_corpus_gather(const flmr_corpus_t* c, const int64_t* d_pids, int64_t n_pids, int nd_max,
+                       void* d_out_bf16, uint8_t* d_mask, void* stream) {
+  if (!c || !d_pids || !d_out_bf16) return fail(FLMR_ERR_INVALID_ARG, "null argument");
+  if (n_pids < 0 || nd_max < 1) return fail(FLMR_ERR_INVALID_ARG, "bad shape n_pids=%lld nd_max=%d", (long long)n_pids, nd_max);
+  if (n_pids == 0) return FLMR_OK;
+  DeviceGuard guard(c->device);
+  if (!guard.ok) return fail(FLMR_ERR_CUDA, "cudaSetDevice(%d) failed", c->device);
+  const int threads = 256;
+  const int64_t blocks = (n_pids * nd_max * 32 + threads - 1) / threads;
+  if (blocks > 0x7fffffffll) return fail(FLMR_ERR_UNSUPPORTED, "gather of %lld x %d rows is too large", (long long)n_pids, nd_max);
+  flmr_gather_kernel<<<static_cast<unsigned>(blocks), threads, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const uint2*>(c->d_tokens), c->d_poff, c->d_doclen, d_pids, n_pids, nd_max,
+      c->n_passages, c->pid_base, static_cast<uint2*>(d_out_bf16), d_mask);
+  FLMR_CUDA(cudaGetLastError());
+  ++g_launches;
+  return FLMR_OK;
+}
+
 int flmr_maxsim_argmax(const void* d_q, int n_queries, int nq, const void* d_docs,
                        const uint8_t* d_mask, int n_docs, int nd, int32_t* d_argmax, float* d_rowmax,
                        int device, void* stream) {

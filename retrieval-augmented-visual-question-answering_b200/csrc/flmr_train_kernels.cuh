@@ -167,4 +167,25 @@ __global__ void flmr_bwd_dd_kernel(const __nv_bfloat16* __restrict__ q, const in
   for (int e = 0; e < 4; ++e) atomicAdd(dst + e, gp * f[e]);
 }
 
+// Padded batch of retrieved passages out of the resident corpus.  One warp per (slot, token row).
+__global__ void flmr_gather_kernel(const uint2* __restrict__ tokens, const int64_t* __restrict__ poff,
+                                   const int32_t* __restrict__ doclen, const int64_t* __restrict__ pids,
+                                   int64_t n_pids, int nd_max, int64_t n_passages, int64_t pid_base,
+                                   uint2* __restrict__ out, uint8_t* __restrict__ mask) {
+  const int64_t w = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= n_pids * nd_max) return;
+  const int64_t slot = w / nd_max;
+  const int j = static_cast<int>(w % nd_max);
+  const int64_t p = pids[slot] - pid_base;
+  uint2 v = make_uint2(0u, 0u);
+  bool real = false;
+  if (p >= 0 && p < n_passages && j < doclen[p]) {
+    v = tokens[(poff[p] + j) * 32 + lane];
+    real = true;
+  }
+  out[w * 32 + lane] = v;
+  if (mask && lane == 0) mask[w] = real ? 1 : 0;
+}
+
 }  // namespace flmr

@@ -142,6 +142,33 @@ class Searcher:
             outp.append(pids)
         return torch.cat(outs), torch.cat(outp)
 
+    def retrieve_and_rescore(self, Q: torch.Tensor, n_docs: int, generator: Optional[torch.Generator] = None):
+        """The retrieval block of ``RagModelForBlip.main_retrieve`` (src/models/rag/rag_model_blip.py:388-443)
+        in one call: search ``max(5, n_docs)`` passages per query (:392-397), keep ``n_docs`` of them (a random
+        subset when ``n_docs < 5``, as :411-412 does with ``random.sample``), fetch their token embeddings and
+        re-score them with the differentiable ``score`` so the gradient reaches the query encoder (:430-435).
+
+        ``Q [B, Nq, d]`` stays on the GPU; the retrieved embeddings are gathered out of the resident corpus
+        (no host dictionary, no H2D copy).  Returns a dict with ``doc_scores [B, n_docs]`` (differentiable
+        w.r.t. ``Q``), ``retrieved_doc_ids`` (int64 numpy ``[B, n_docs]``, as :441), ``search_scores``, and the
+        gathered ``item_embeddings [B, n_docs, Nd, d]`` / ``item_mask [B, n_docs, Nd, 1]``."""
+        from .modeling import colbert_score
+        if Q.dim() != 3:
+            raise ValueError("Q must be [B, Nq, d]")
+        n_retrieve = max(5, int(n_docs))
+        Qd = Q.to(self.corpus.device)
+        s, p = self._search_tensors(Qd.detach(), n_retrieve)
+        if s.size(1) < n_docs:
+            raise ValueError("the corpus holds %d passages, fewer than n_docs=%d" % (s.size(1), n_docs))
+        if s.size(1) != n_docs:
+            pick = torch.rand(s.shape, generator=generator, device="cpu").argsort(dim=1)[:, :n_docs].to(s.device)
+            s, p = s.gather(1, pick), p.gather(1, pick)
+        D, mask = self.corpus.gather_padded(p)                               # [B, n_docs, Nd, d]
+        doc_scores = torch.stack([
+            colbert_score(Qd[b:b + 1].repeat_interleave(n_docs, dim=0), D[b], mask[b]) for b in range(Qd.size(0))])
+        return {"doc_scores": doc_scores, "retrieved_doc_ids": p.cpu().numpy(), "search_scores": s,
+                "item_embeddings": D, "item_mask": mask}
+
     def dense_search(self, Q: torch.Tensor, k: int = 10, filter_fn=None, remove_zero_tensors: bool = False):
         """searcher.py:91-132 -> ``(pids[:k], [1..k], scores[:k])`` for ONE query ``Q [1, Nq, d]``.
 
