@@ -1089,9 +1089,16 @@ int flmr_maxsim_argmax(const void* d_q, int n_queries, int nq, const void* d_doc
   if (!guard.ok) return fail(FLMR_ERR_CUDA, "cudaSetDevice(%d) failed", device);
   dim3 grid(static_cast<unsigned>((nq + kArgTile - 1) / kArgTile), static_cast<unsigned>(n_docs),
             static_cast<unsigned>(n_queries));
-  flmr_argmax_kernel<<<grid, kArgThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(d_q), static_cast<const __nv_bfloat16*>(d_docs), d_mask, nq, nd,
-      n_docs, d_argmax, d_rowmax);
+  // warp-MMA kernel by default; FLMR_ARGMAX_SIMT=1 selects the plain-FMA twin (cross-check / A-B timing)
+  const char* simt = getenv("FLMR_ARGMAX_SIMT");
+  if (simt && atoi(simt))
+    flmr_argmax_kernel<<<grid, kArgThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(d_q), static_cast<const __nv_bfloat16*>(d_docs), d_mask, nq, nd,
+        n_docs, d_argmax, d_rowmax);
+  else
+    flmr_argmax_mma_kernel<<<grid, kMmaThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(d_q), static_cast<const __nv_bfloat16*>(d_docs), d_mask, nq, nd,
+        n_docs, d_argmax, d_rowmax);
   FLMR_CUDA(cudaGetLastError());
   ++g_launches;
   return FLMR_OK;

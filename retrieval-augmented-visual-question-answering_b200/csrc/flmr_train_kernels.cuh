@@ -125,6 +125,122 @@ flmr_argmax_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __r
   }
 }
 
+// ---- the same contract on the warp-level tensor-core path (mma.sync m16n8k16, bf16 -> fp32) -------------
+// Training shapes are far too small to amortise the tcgen05 machinery of the scan kernel (TMEM allocation,
+// TMA descriptors, a persistent grid), but the legacy warp MMA is still several times the SIMT FMA rate.
+// CTA = 4 warps x 16 query rows; the query tile's A fragments are loaded once (ldmatrix) and stay in
+// registers for every 64-token chunk of the document.
+constexpr int kMmaThreads = 128;
+constexpr int kMmaStride = 136;     // bf16 per staged row: 272 B, 16-B aligned rows, conflict-free ldmatrix
+
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], const void* smem_ptr) {
+  const uint32_t addr = static_cast<uint32_t>(__cvta_generic_to_shared(smem_ptr));
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr));
+}
+
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+               "{%0, %1, %2, %3};\n"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+__global__ void __launch_bounds__(kMmaThreads)
+flmr_argmax_mma_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ d,
+                       const uint8_t* __restrict__ mask, int nq, int nd, int n, int32_t* __restrict__ arg,
+                       float* __restrict__ rowmax) {
+  __shared__ __align__(16) __nv_bfloat16 qs[kArgTile * kMmaStride];
+  __shared__ __align__(16) __nv_bfloat16 ds[kArgTile * kMmaStride];
+  __shared__ uint8_t ms[kArgTile];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int i0 = blockIdx.x * kArgTile, p = blockIdx.y, b = blockIdx.z;
+  const __nv_bfloat16* qb = q + (static_cast<int64_t>(b) * nq + i0) * 128;
+  const __nv_bfloat16* db = d + static_cast<int64_t>(p) * nd * 128;
+  const uint8_t* mp = mask + static_cast<int64_t>(p) * nd;
+
+  for (int t = tid; t < kArgTile * 16; t += kMmaThreads) {     // 16 uint4 (8 bf16) per row
+    const int r = t >> 4, c = t & 15;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (i0 + r < nq) v = *reinterpret_cast<const uint4*>(qb + static_cast<int64_t>(r) * 128 + c * 8);
+    *reinterpret_cast<uint4*>(qs + r * kMmaStride + c * 8) = v;
+  }
+  __syncthreads();
+  uint32_t a[8][4];                                            // this warp's 16 rows x K = 128
+  {
+    const int row = warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+    const int kc = (lane >> 4) * 8;
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks) ldmatrix_x4(a[ks], qs + row * kMmaStride + ks * 16 + kc);
+  }
+  float best[2] = {-INFINITY, -INFINITY};                      // rows g and g + 8 of the warp's 16
+  int barg[2] = {-1, -1};
+  for (int j0 = 0; j0 < nd; j0 += kArgTile) {
+    __syncthreads();                                           // previous chunk fully consumed
+    for (int t = tid; t < kArgTile * 16; t += kMmaThreads) {
+      const int r = t >> 4, c = t & 15;
+      uint4 v = make_uint4(0u, 0u, 0u, 0u);
+      if (j0 + r < nd) v = *reinterpret_cast<const uint4*>(db + static_cast<int64_t>(j0 + r) * 128 + c * 8);
+      *reinterpret_cast<uint4*>(ds + r * kMmaStride + c * 8) = v;
+    }
+    if (tid < kArgTile) ms[tid] = (j0 + tid < nd) ? mp[j0 + tid] : 0;
+    __syncthreads();
+    float acc[8][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[nt][e] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks) {
+#pragma unroll
+      for (int np = 0; np < 4; ++np) {                         // two 8-token tiles per ldmatrix.x4
+        uint32_t bf[4];
+        const int tok = np * 16 + (lane & 7) + ((lane >> 4) & 1) * 8;
+        const int kc = ks * 16 + ((lane >> 3) & 1) * 8;
+        ldmatrix_x4(bf, ds + tok * kMmaStride + kc);
+        mma_bf16_16816(acc[2 * np], a[ks], bf[0], bf[1]);
+        mma_bf16_16816(acc[2 * np + 1], a[ks], bf[2], bf[3]);
+      }
+    }
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt)                             // this thread's columns ascend: '>' keeps the first
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int jl = nt * 8 + 2 * (lane & 3) + e;
+        if (ms[jl]) {
+          if (acc[nt][e] > best[0]) {
+            best[0] = acc[nt][e];
+            barg[0] = j0 + jl;
+          }
+          if (acc[nt][2 + e] > best[1]) {
+            best[1] = acc[nt][2 + e];
+            barg[1] = j0 + jl;
+          }
+        }
+      }
+  }
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {                                // combine the 4 column owners of a row
+#pragma unroll
+    for (int off = 1; off <= 2; off <<= 1) {
+      const float ob = __shfl_xor_sync(0xffffffffu, best[r], off);
+      const int oa = __shfl_xor_sync(0xffffffffu, barg[r], off);
+      const bool take = oa >= 0 && (barg[r] < 0 || ob > best[r] || (ob == best[r] && oa < barg[r]));
+      if (take) {
+        best[r] = ob;
+        barg[r] = oa;
+      }
+    }
+    const int i = i0 + warp * 16 + (lane >> 2) + r * 8;
+    if ((lane & 3) == 0 && i < nq) {
+      const int64_t o = (static_cast<int64_t>(b) * n + p) * nq + i;
+      arg[o] = barg[r];
+      if (rowmax) rowmax[o] = best[r];
+    }
+  }
+}
+
 // dQ[b, i, :] = sum_p g[b, p] * D[p, arg[b, p, i], :].  One warp per (b, i), 4 dims per lane.
 __global__ void flmr_bwd_dq_kernel(const __nv_bfloat16* __restrict__ d, const int32_t* __restrict__ arg,
                                    const float* __restrict__ g, int B, int nq, int n, int nd,
