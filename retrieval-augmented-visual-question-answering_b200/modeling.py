@@ -33,8 +33,8 @@ from .maxsim import maxsim_argmax, maxsim_backward, maxsim_scores
 # Below this many multiply-accumulates the whole forward is ONE launch of the arg-max kernel (scores =
 # row maxima summed), which also saves the winners for the backward; above it the tcgen05 scan kernel over
 # a temporary packed corpus wins despite its per-call setup (allocation, partition build, TMA descriptor:
-# ~2 ms measured, profiles/r01_train_step_probe.md) and the backward recomputes the winners.
-_FUSED_SMALL_MAX_MACS = 3e10
+# ~2.3 ms measured against ~5e13 MAC/s of the warp-MMA kernel, profiles/r01_train_step_probe.md) and the backward recomputes the winners.
+_FUSED_SMALL_MAX_MACS = 1e11
 
 
 def _forward_scores(Q: torch.Tensor, D_padded: torch.Tensor, D_mask: torch.Tensor):
