@@ -150,3 +150,64 @@ def test_fused_small_forward_and_scan_kernel_forward_agree(monkeypatch):
     np.testing.assert_allclose(outs[0][1].cpu().numpy(), outs[1][1].cpu().numpy(), rtol=1e-5, atol=1e-6)
     np.testing.assert_allclose(outs[0][2].cpu().numpy(), outs[1][2].cpu().numpy(), rtol=1e-5, atol=1e-6)
     np.testing.assert_allclose(outs[0][0].cpu().numpy(), _ref_all_pairs(Q, D, mask).cpu().numpy(), rtol=2e-5)
+
+
+# ---- cross-rank in-batch negatives over NCCL (needs >= 2 GPUs; skipped on a single-GPU box) ---------------
+def _nccl_ib_worker(rank, world, port, ret):
+    import os
+    import torch.distributed as dist
+    import ravqa_b200 as R
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    B, nway, nq = 3, 2, 40
+    nds = [30 + 9 * r for r in range(world)]                   # ranks pad their documents differently
+
+    def make(r):
+        g = torch.Generator().manual_seed(200 + r)
+        Q = torch.nn.functional.normalize(torch.randn(B, nq, 128, generator=g), dim=-1).bfloat16().float()
+        D = torch.nn.functional.normalize(torch.randn(B * nway, nds[r], 128, generator=g), dim=-1).bfloat16().float()
+        lens = torch.randint(4, nds[r] + 1, (B * nway,), generator=g)
+        m = torch.arange(nds[r])[None, :] < lens[:, None]
+        return Q.cuda(rank), (D * m[..., None]).cuda(rank), m.cuda(rank)
+
+    Q, D, m = make(rank)
+    Q.requires_grad_(True)
+    D.requires_grad_(True)
+    loss, S = R.in_batch_negatives_loss(Q, D, m.unsqueeze(-1), nway, return_scores=True, cross_rank_negatives=True)
+    loss.backward()
+    # single-process torch restatement of the global batch
+    parts = [make(r) for r in range(world)]
+    Qs = [p[0].clone().requires_grad_(True) for p in parts]
+    Ds = [p[1].clone().requires_grad_(True) for p in parts]
+    nd_max = max(nds)
+    Dg = torch.cat([torch.nn.functional.pad(d, (0, 0, 0, nd_max - d.size(1))) for d in Ds])
+    Mg = torch.cat([torch.nn.functional.pad(p[2], (0, nd_max - p[2].size(1))) for p in parts])
+    losses = []
+    for r in range(world):
+        losses.append(torch.nn.functional.cross_entropy(
+            _ref_all_pairs(Qs[r], Dg, Mg), r * B * nway + torch.arange(B, device=Dg.device) * nway))
+    sum(losses).backward()
+    ok = (S.shape == (B, world * B * nway)
+          and torch.allclose(loss.detach(), losses[rank].detach(), rtol=1e-5, atol=1e-6)
+          and torch.allclose(Q.grad, Qs[rank].grad, rtol=1e-3, atol=1e-6)
+          and torch.allclose(D.grad, Ds[rank].grad, rtol=1e-3, atol=1e-6))
+    ret[rank] = bool(ok)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_cross_rank_negatives_nccl():
+    import socket
+    import torch.multiprocessing as mp
+    world = min(torch.cuda.device_count(), 4)
+    if world < 2:
+        pytest.skip("needs >= 2 GPUs")
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ret = mp.Manager().dict()
+    mp.spawn(_nccl_ib_worker, args=(world, port, ret), nprocs=world, join=True)
+    assert dict(ret) == {r: True for r in range(world)}
