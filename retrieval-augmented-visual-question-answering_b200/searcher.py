@@ -67,12 +67,14 @@ def _query_keys(queries, n: int) -> List:
 
 class Searcher:
     def __init__(self, index: Union[str, FlatCorpus], checkpoint=None, collection=None, config=None,
-                 disable_gpu: bool = False, device: Optional[Union[int, torch.device]] = None,
+                 disable_gpu: bool = True, device: Optional[Union[int, torch.device]] = None,
                  encode_fn: Optional[Callable] = None, index_root: Optional[str] = None,
                  query_batch: int = 64):
-        if disable_gpu:
-            raise RuntimeError("this Searcher IS the GPU path; there is no CPU fallback "
-                               "(the reference forced CPU search under DDP, FLMR_executor.py:778-781)")
+        # `disable_gpu` is part of the reference signature (default True) but dead there: colbert/searcher.py:23
+        # never reads it, the device is chosen by config.total_visible_gpus (:40-43), which FLMR_executor.py:778-781
+        # zeroes under DDP to force CPU search.  Here the search always runs on the GPU (no CPU path exists);
+        # FlatCorpus raises when CUDA is absent.
+        del disable_gpu
         self.config = config
         self.checkpoint = checkpoint
         self.collection = collection
