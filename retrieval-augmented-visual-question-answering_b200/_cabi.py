@@ -71,6 +71,7 @@ def lib() -> C.CDLL:
     L.flmr_last_error.restype = C.c_char_p
     L.flmr_last_error.argtypes = []
     L.flmr_abi_version.restype = i32
+    L.flmr_abi_version.argtypes = []
     L.flmr_corpus_create.argtypes = [vp, vp, i64, i32, i32, i64, u32, C.POINTER(vp)]
     L.flmr_corpus_destroy.argtypes = [vp]
     L.flmr_corpus_info.argtypes = [vp, C.POINTER(CorpusInfo)]

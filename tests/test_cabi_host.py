@@ -27,6 +27,32 @@ def test_library_exports_every_declared_symbol():
     assert L.flmr_abi_version() == 1
 
 
+def header_prototypes():
+    """{name: number of parameters} for every function the header declares."""
+    text = open(os.path.join(ROOT, "include", "flmr_maxsim.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    out = {}
+    for name, params in re.findall(r"\b(flmr_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", text):
+        params = params.strip()
+        out[name] = 0 if params in ("", "void") else params.count(",") + 1
+    return out
+
+
+def test_ctypes_prototypes_match_the_header():
+    """Every binding in _cabi.py (and the stub shown in INTEGRATION.md) passes exactly the arguments the
+    header declares — a mismatch would corrupt the call silently (ctypes cannot check C prototypes)."""
+    L = _cabi.lib()
+    protos = header_prototypes()
+    assert set(protos) == set(_cabi.SYMBOLS)
+    for name, n_params in protos.items():
+        argtypes = getattr(L, name).argtypes
+        assert argtypes is not None, name + " has no argtypes"
+        assert len(argtypes) == n_params, "%s: header has %d parameters, ctypes %d" % (name, n_params, len(argtypes))
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    for name, n_list in re.findall(r"L\.(flmr_[a-z0-9_]+)\.argtypes\s*=\s*\[([^\]]*)\]", doc):
+        assert n_list.count(",") + 1 == protos[name], "INTEGRATION.md stub of %s is out of date" % name
+
+
 def test_library_is_sm100a_tcgen05_build():
     import subprocess
     from ravqa_b200 import build
