@@ -370,8 +370,10 @@ flmr_scan_kernel(const __grid_constant__ CUtensorMap tmap_d, const ScanParams p)
       const uint64_t b_desc0 = make_kmajor_sw128_desc(smem_base + S::kOffD + s * kDTileBytes);
       const uint32_t a_first = static_cast<uint32_t>(t) * n_mtiles;
 #pragma unroll 1
+      const bool rot = ((n_mtiles & t) & 1) != 0;  // odd tile, odd tile count: rotated order (see epilogue)
       for (uint32_t a = a_first + ((a_first ^ iw) & 1u); a < a_first + n_mtiles; a += 2) {
-        const uint32_t mt = a - a_first;
+        const uint32_t j = a - a_first;
+        const uint32_t mt = rot ? (j == 0 ? static_cast<uint32_t>(n_mtiles) - 1u : j - 1u) : j;
         const uint32_t as = a & stage_mask, aph = (a >> stage_shift) & 1u;  // TMEM stage / phase
         if (dbg != 4 && dbg != 5) {  // (modes 4/5: never wait for the epilogue)
           mbar_wait(bar_t_empty(as), aph ^ 1u, p.status, kDevTimeoutMma);
@@ -401,10 +403,13 @@ flmr_scan_kernel(const __grid_constant__ CUtensorMap tmap_d, const ScanParams p)
     }
   } else if (warp < kEpiWarps) {
     // ===================== epilogue (TMEM drain) =====================
-    // Accumulators are numbered in MMA issue order, a = t * n_mtiles + mt; warpgroup g drains the
+    // Accumulators are numbered in MMA issue order, a = t * n_mtiles + j; warpgroup g drains the
     // accumulators with (a & 1) == g, so the two warpgroups alternate strictly.  The running max of
-    // the passage straddling D tiles is per (query tile, row): when n_mtiles is odd it changes
-    // hands between the warpgroups every tile, through shared memory + a version flag.
+    // the passage straddling D tiles is per (query tile, row) and must follow the query tile from D
+    // tile to D tile.  With an even tile count query tile mt = j always meets the same warpgroup.
+    // With an odd count the issue order of odd D tiles is rotated (j = 0 is the LAST query tile, j > 0
+    // is tile j - 1): query tiles 0 .. n_mtiles-2 then keep their warpgroup and only the last one
+    // changes hands every D tile (shared memory + mbarrier), instead of all of them.
     const int wg = warp >> 2;         // epilogue warp 0..7 -> warpgroup 0/1
     const int quad = warp & 3;        // TMEM lane quadrant this warp may access
     const uint32_t lane_base = static_cast<uint32_t>(quad * 32) << 16;
@@ -451,14 +456,17 @@ flmr_scan_kernel(const __grid_constant__ CUtensorMap tmap_d, const ScanParams p)
                 kDevTimeoutEpilogue);
       const uint32_t a_first = static_cast<uint32_t>(t) * n_mtiles;
 #pragma unroll 1
+      const bool rot = ((n_mtiles & t) & 1) != 0;
       for (uint32_t a = a_first + ((a_first ^ static_cast<uint32_t>(wg)) & 1u); a < a_first + n_mtiles;
            a += 2) {
-        const int mt = static_cast<int>(a - a_first);
+        const int j = static_cast<int>(a - a_first);
+        const int mt = rot ? (j == 0 ? n_mtiles - 1 : j - 1) : j;
+        const bool crosses = carry_crosses && mt == n_mtiles - 1;
         const uint32_t as = a & stage_mask, aph = (a >> stage_shift) & 1u;  // TMEM stage / phase
         // running max handed over by whoever drained (t-1, mt): with an odd number of query tiles
         // that is the other warpgroup (mbarrier arrive/wait = release/acquire); with an even number
         // it is this very warp, and program order suffices
-        if (carry_crosses && t > 0)
+        if (crosses && t > 0)
           mbar_wait(bar_carry(mt, quad), static_cast<uint32_t>(t - 1) & 1u, p.status,
                     kDevTimeoutEpilogue);
         float m = carry[mt * kTileM];
@@ -496,7 +504,7 @@ flmr_scan_kernel(const __grid_constant__ CUtensorMap tmap_d, const ScanParams p)
         }
         if (quad == 0 && lane == 0) dbg_stamp<kDebug>(p, cta, a, 6);               // chunk processing done
         carry[mt * kTileM] = m;
-        if (carry_crosses) {
+        if (crosses) {
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_carry(mt, quad));
         }
