@@ -234,6 +234,15 @@ def run_reference(args):
         "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    # also report the reference's PRUNED search (what its executors actually run; approximate ranking) when a
+    # GPU is there to build the sample PLAID index quickly with torch ops — the timed search itself is CPU-only
+    if not args.no_plaid_baseline:
+        try:
+            import torch
+            if torch.cuda.is_available():
+                line["cpu_baseline_plaid"] = cpu_plaid_rate(args, "cuda:0")
+        except Exception as e:
+            line["cpu_baseline_plaid"] = {"value": None, "unit": UNIT, "kind": "error", "sample": repr(e)}
     print(json.dumps(line), flush=True)
 
 
