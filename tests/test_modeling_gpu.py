@@ -211,3 +211,27 @@ def test_cross_rank_negatives_nccl():
     ret = mp.Manager().dict()
     mp.spawn(_nccl_ib_worker, args=(world, port, ret), nprocs=world, join=True)
     assert dict(ret) == {r: True for r in range(world)}
+
+
+def test_training_path_matches_reference_autograd_golden():
+    """Loss, aligned scores and gradients vs tests/golden/train_ib_loss.npz — outputs of the reference's own
+    compute_ib_loss_new / ColBERT.score and torch autograd (tests/golden/make_golden_train.py); the mask has
+    punctuation-style holes."""
+    import os
+    import ravqa_b200 as R
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "train_ib_loss.npz"))
+    f32 = lambda bits: torch.from_numpy((bits.astype(np.uint32) << 16).view(np.float32).copy())
+    Q, D, nway = f32(z["Q_bf16"]).cuda(), f32(z["D_bf16"]).cuda(), int(z["nway"])
+    mask = torch.from_numpy(z["mask"]).cuda().unsqueeze(-1)
+    Qg, Dg = Q.clone().requires_grad_(True), D.clone().requires_grad_(True)
+    loss = R.in_batch_negatives_loss(Qg, Dg, mask, nway)
+    loss.backward()
+    np.testing.assert_allclose(loss.item(), float(z["ib_loss"]), rtol=5e-6)
+    np.testing.assert_allclose(Qg.grad.cpu().numpy(), z["ib_dQ"], rtol=1e-3, atol=1e-6)
+    np.testing.assert_allclose(Dg.grad.cpu().numpy(), z["ib_dD"], rtol=1e-3, atol=1e-6)
+    Q2, D2 = Q.clone().requires_grad_(True), D.clone().requires_grad_(True)
+    s = R.FLMRModelForRetrieval(nway=nway).score(Q2.repeat_interleave(nway, dim=0).contiguous(), D2, mask)
+    np.testing.assert_allclose(s.detach().cpu().numpy(), z["scores"], rtol=2e-5)
+    (s * torch.from_numpy(z["score_weights"]).cuda()).sum().backward()
+    np.testing.assert_allclose(Q2.grad.cpu().numpy(), z["score_dQ"], rtol=1e-3, atol=1e-6)
+    np.testing.assert_allclose(D2.grad.cpu().numpy(), z["score_dD"], rtol=1e-3, atol=1e-6)

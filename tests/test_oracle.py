@@ -111,3 +111,27 @@ def test_reference_extension_agrees_when_present():
     scores = rng.standard_normal((int(lengths.sum()), 33)).astype(np.float32)
     ref = mod.segmented_maxsim_cpp(torch.from_numpy(scores), torch.from_numpy(lengths).long()).numpy()
     np.testing.assert_allclose(O.segmented_maxsim(scores, lengths), ref, rtol=1e-6, atol=1e-5)
+
+
+def test_training_path_restatement_matches_reference_autograd():
+    """oracle ib_loss_and_grads / maxsim_grads vs tests/golden/train_ib_loss.npz, produced by the reference's
+    own compute_ib_loss_new / score and torch autograd (tests/golden/make_golden_train.py)."""
+    import os
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "train_ib_loss.npz"))
+    f32 = lambda bits: (bits.astype(np.uint32) << 16).view(np.float32)
+    Q, D, mask, nway = f32(z["Q_bf16"]), f32(z["D_bf16"]), z["mask"], int(z["nway"])
+    loss, dQ, dD, S = O.ib_loss_and_grads(Q, D, mask, nway)
+    np.testing.assert_allclose(loss, z["ib_loss"], rtol=2e-6)
+    np.testing.assert_allclose(dQ, z["ib_dQ"], rtol=1e-4, atol=2e-7)
+    np.testing.assert_allclose(dD, z["ib_dD"], rtol=1e-4, atol=2e-7)
+    assert (dD[~mask] == 0).all()
+    # aligned scores of the training forward (Q repeat_interleave'd) and their gradients
+    rows = np.repeat(np.arange(Q.shape[0]), nway)
+    cols = np.arange(D.shape[0])
+    np.testing.assert_allclose(S[rows, cols], z["scores"], rtol=2e-6)
+    dS = np.zeros_like(S)
+    dS[rows, cols] = z["score_weights"]
+    _, arg = O.all_pairs_scores(Q, D, mask)
+    dQ2, dD2 = O.maxsim_grads(Q, D, arg, dS)
+    np.testing.assert_allclose(dQ2, z["score_dQ"], rtol=1e-4, atol=2e-7)
+    np.testing.assert_allclose(dD2, z["score_dD"], rtol=1e-4, atol=2e-7)
