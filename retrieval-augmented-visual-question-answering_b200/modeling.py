@@ -81,6 +81,20 @@ class _AllPairsMaxSim(torch.autograd.Function):
                 dD.to(D_padded.dtype) if dD is not None else None, None)
 
 
+def _consecutive_runs(Q: torch.Tensor):
+    """Runs of identical consecutive queries: (one representative per run ``[U, Nq, d]``, run index of every
+    row ``[n]``).  Same result as ``torch.unique_consecutive(Q, dim=0, return_inverse=True)``, whose CUDA
+    implementation compares whole rows (Nq*d elements) serially in a single thread — ~80 ms per call for an
+    832-token query, measured — where two vectorised passes take microseconds."""
+    n = Q.size(0)
+    if n == 1:
+        return Q, torch.zeros(1, dtype=torch.long, device=Q.device)
+    new_run = torch.ones(n, dtype=torch.bool, device=Q.device)
+    new_run[1:] = (Q[1:] != Q[:-1]).flatten(1).any(dim=1)
+    inverse = torch.cumsum(new_run.long(), dim=0) - 1
+    return Q[new_run], inverse
+
+
 class _AlignedMaxSim(torch.autograd.Function):
     """scores[p] = MaxSim(Q[p], D[p]) for ``Q [n, Nq, d]`` aligned with ``D [n, Nd, d]``.
 
@@ -90,7 +104,7 @@ class _AlignedMaxSim(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, Q: torch.Tensor, D_padded: torch.Tensor, D_mask: torch.Tensor) -> torch.Tensor:
-        Qu, inverse = torch.unique_consecutive(Q.detach(), dim=0, return_inverse=True)
+        Qu, inverse = _consecutive_runs(Q.detach())
         S, mask, arg = _forward_scores(Qu, D_padded, D_mask)
         cols = torch.arange(D_padded.size(0), device=S.device)
         ctx.has_arg = arg is not None

@@ -154,7 +154,7 @@ class Searcher:
         (no host dictionary, no H2D copy).  Returns a dict with ``doc_scores [B, n_docs]`` (differentiable
         w.r.t. ``Q``), ``retrieved_doc_ids`` (int64 numpy ``[B, n_docs]``, as :441), ``search_scores``, and the
         gathered ``item_embeddings [B, n_docs, Nd, d]`` / ``item_mask [B, n_docs, Nd, 1]``."""
-        from .modeling import colbert_score
+        from .modeling import all_pairs_maxsim, colbert_score
         if Q.dim() != 3:
             raise ValueError("Q must be [B, Nq, d]")
         n_retrieve = max(5, int(n_docs))
@@ -166,8 +166,16 @@ class Searcher:
             pick = torch.rand(s.shape, generator=generator, device="cpu").argsort(dim=1)[:, :n_docs].to(s.device)
             s, p = s.gather(1, pick), p.gather(1, pick)
         D, mask = self.corpus.gather_padded(p)                               # [B, n_docs, Nd, d]
-        doc_scores = torch.stack([
-            colbert_score(Qd[b:b + 1].repeat_interleave(n_docs, dim=0), D[b], mask[b]) for b in range(Qd.size(0))])
+        B = Qd.size(0)
+        if B <= 16:
+            # one launch: every question against every retrieved passage, keep the block diagonal (the extra
+            # pairs cost less than B separate launches; their upstream gradient is zero and is skipped)
+            S = all_pairs_maxsim(Qd, D.flatten(0, 1), mask.flatten(0, 1))    # [B, B * n_docs]
+            cols = torch.arange(B, device=S.device)[:, None] * n_docs + torch.arange(n_docs, device=S.device)
+            doc_scores = S.gather(1, cols)
+        else:
+            doc_scores = torch.stack([
+                colbert_score(Qd[b:b + 1].repeat_interleave(n_docs, dim=0), D[b], mask[b]) for b in range(B)])
         return {"doc_scores": doc_scores, "retrieved_doc_ids": p.cpu().numpy(), "search_scores": s,
                 "item_embeddings": D, "item_mask": mask}
 
