@@ -21,6 +21,11 @@ int main(void) {
   if (flmr_maxsim_topk(NULL, NULL, NULL, 1, 32, 5, 0, NULL, NULL, NULL) != FLMR_ERR_INVALID_ARG) return 13;
   if (flmr_topk_select(NULL, 1, 10, 5, 0, NULL, NULL, 0, NULL) != FLMR_ERR_INVALID_ARG) return 14;
   if (flmr_corpus_destroy(NULL) != FLMR_OK || flmr_workspace_destroy(NULL) != FLMR_OK) return 15;
+  /* training / RAG entry points: argument validation happens before any CUDA call */
+  if (flmr_maxsim_argmax(NULL, 1, 32, NULL, NULL, 1, 8, NULL, NULL, 0, NULL) != FLMR_ERR_INVALID_ARG) return 17;
+  if (flmr_maxsim_backward(NULL, 1, 32, NULL, 1, 8, NULL, NULL, NULL, NULL, 0, NULL) != FLMR_ERR_INVALID_ARG) return 18;
+  if (flmr_corpus_gather(NULL, NULL, 1, 8, NULL, NULL, NULL) != FLMR_ERR_INVALID_ARG) return 19;
+  if (flmr_plaid_decode(NULL, NULL, 1, NULL, 1, NULL, 2, FLMR_DIM, 1, NULL, 0, NULL) != FLMR_ERR_INVALID_ARG) return 20;
   /* host-only helper: 5 passages over 2 CTAs */
   int32_t dl[5] = {100, 7, 96, 1, 50};
   int32_t row_begin[3];
