@@ -10,14 +10,16 @@
 // `scores.sort()` of IndexScorer.rank (CB/search/index_storage.py:95).
 //
 // Structure (one persistent CTA per SM, 12 warps, warp-specialised; accumulators are numbered in
-// tile-major issue order, a = t * n_mtiles + mt):
+// issue order, a = t * n_mtiles + j, where j-th in D tile t is query tile mt = j — except that with an
+// odd tile count the odd D tiles start with the LAST query tile, see the epilogue):
 //   warps 0..7   : epilogue, two warpgroups; warpgroup g drains the accumulators with (a & 1) == g.
 //                  TMEM lane = query token, TMEM column = passage token: the max over a passage's
 //                  tokens is a per-thread running max over columns (FMNMX3, no shuffles); at a passage
 //                  end (bit in the tile's end mask) the warp sums its 32 lanes and lane 0 stores one
 //                  partial per (32-row block, passage).  The running max of the passage straddling
-//                  two D tiles lives in shared memory per (query tile, row) and, when n_mtiles is
-//                  odd, changes hands between the warpgroups through an mbarrier.
+//                  two D tiles lives in shared memory per (query tile, row); when n_mtiles is odd the
+//                  last query tile's changes hands between the warpgroups through an mbarrier (all
+//                  other query tiles always meet the same warpgroup thanks to the rotated order).
 //   warp 8       : reducer.  Per D tile (mbarrier-fed, double-buffered partials): per (query, passage
 //                  ending in the tile) sums the row-block partials in fixed order (deterministic),
 //                  optionally accumulates / stores scores to HBM, and maintains the per-CTA top-k.
@@ -354,7 +356,7 @@ flmr_scan_kernel(const __grid_constant__ CUtensorMap tmap_d, const ScanParams p)
     // A single thread needs ~31 cycles per tcgen05.mma issue plus ~300 cycles of wait / fence /
     // commit per accumulator -- more than the 384 cycles the 8 MMAs of an accumulator execute
     // (profiles/r01_handoff_timeline.md).  So TWO warps issue: issuer i owns the accumulators with
-    // a = i (mod 2) in tile-major order (a = t * n_mtiles + mt), i.e. with two TMEM stages each
+    // a = i (mod 2) in issue order (a = t * n_mtiles + j), i.e. with two TMEM stages each
     // issuer is bound to one stage and to the epilogue warpgroup that drains it.  Loops are
     // warp-uniform; one elected lane (always the same one) issues tcgen05.mma / commit so the
     // descriptors stay in uniform registers.
