@@ -227,6 +227,13 @@ int flmr_debug_build_partition(const int32_t* h_doclens, int64_t n_passages, int
                                uint32_t* tile_end_mask, int32_t* tile_first_pid,
                                int64_t tile_capacity, int64_t* n_tiles_out);
 
+/* Test infrastructure, host-only: the corpus passes flmr_maxsim_scores / flmr_maxsim_topk run for a batch of
+ * `n_queries` queries of `nq` tokens (a pass = one scan-kernel launch with up to 640 query rows resident).
+ * out_plan (may be NULL to query *n_passes_out) receives 8 int32 per pass: first query, queries resident,
+ * first row, rows, 32-row blocks per query, 128-row tiles, flags (1 = adds earlier partial scores,
+ * 2 = stores partial scores, 4 = final: scores complete, top-k taken), first query of its partial-score rows. */
+int flmr_debug_plan_passes(int n_queries, int nq, int32_t* out_plan, int capacity, int* n_passes_out);
+
 /* Kernels launched by this library on the calling thread since the last reset (bench evidence). */
 int64_t flmr_launch_count(int reset);
 

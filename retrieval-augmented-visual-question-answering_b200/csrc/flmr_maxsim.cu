@@ -552,6 +552,58 @@ void build_partition(const std::vector<int64_t>& poff, int n_ctas, int tile_n,
   }
 }
 
+// ---- pass planning (pure host logic; exported for tests as flmr_debug_plan_passes) -------------------
+// One pass = one launch of the scan kernel over the whole shard with up to kRbMax 32-row blocks of
+// queries resident (kNqMax queries at most).
+enum : int { kPassAccIn = 1, kPassAccOut = 2, kPassFinal = 4 };
+struct PassPlan {
+  int q_first, n_q;        // queries [q_first, q_first + n_q) are resident
+  int row0, rows;          // their rows [row0, row0 + rows)
+  int rbq, n_mtiles;       // 32-row blocks per query, 128-row MMA tiles of the pass
+  int flags;               // kPassAccIn: add the partial scores of earlier slices; kPassAccOut: store
+                           // partial scores; kPassFinal: scores complete -> top-k (+ all-scores output)
+  int group_first, acc_slot;  // row of the partial-score buffer: query group_first + acc_slot (+ i)
+};
+
+void plan_passes(int n_queries, int nq, std::vector<PassPlan>* out, int* group_out) {
+  out->clear();
+  const int rbq_total = (nq + 31) / 32;
+  if (rbq_total <= kRbMax) {
+    // whole queries resident: as many per pass as fit, spread evenly over the passes that takes (64
+    // queries of one row block: 4 passes of 16 rather than 20+20+20+4, whose short last pass would be
+    // HBM-bound while the others are tensor-bound)
+    const int qpp_max = std::min(kNqMax, kRbMax / rbq_total);
+    const int n_passes = (n_queries + qpp_max - 1) / qpp_max;
+    const int qpp = n_passes ? (n_queries + n_passes - 1) / n_passes : 1;
+    for (int b0 = 0; b0 < n_queries; b0 += qpp) {
+      const int nqp = std::min(qpp, n_queries - b0);
+      out->push_back({b0, nqp, 0, nq, rbq_total, (nqp * rbq_total * 32 + kTileM - 1) / kTileM, kPassFinal,
+                      b0, 0});
+    }
+    *group_out = 1;
+    return;
+  }
+  // queries longer than one pass holds: rows sliced over several passes, partial scores carried through
+  // HBM.  Full slices take one pass per query; the TAIL slices of up to `group` queries share one pass
+  // (Nq = 832: 3 queries = 3 full passes + 1 tail pass instead of 6).
+  const int rows_per_slice = kRbMax * 32;
+  const int n_slices = (nq + rows_per_slice - 1) / rows_per_slice;
+  const int tail_row0 = (n_slices - 1) * rows_per_slice;
+  const int tail_rows = nq - tail_row0;
+  const int tail_rbq = (tail_rows + 31) / 32;
+  const int group = std::max(1, std::min({kNqMax, kRbMax / tail_rbq, n_queries}));
+  for (int b0 = 0; b0 < n_queries; b0 += group) {
+    const int g = std::min(group, n_queries - b0);
+    for (int b = 0; b < g; ++b)
+      for (int s = 0; s + 1 < n_slices; ++s)
+        out->push_back({b0 + b, 1, s * rows_per_slice, rows_per_slice, kRbMax, rows_per_slice / kTileM,
+                        kPassAccOut | (s > 0 ? kPassAccIn : 0), b0, b});
+    out->push_back({b0, g, tail_row0, tail_rows, tail_rbq, (g * tail_rbq * 32 + kTileM - 1) / kTileM,
+                    kPassAccIn | kPassFinal, b0, 0});
+  }
+  *group_out = group;
+}
+
 int launch_scan(const flmr_corpus* c, flmr_workspace* ws, const ScanParams& p, cudaStream_t st) {
   // product instantiation unless a timing experiment / timestamp mode was requested
   // (both instantiations got their dynamic-shared-memory limit raised in flmr_corpus_create)
@@ -649,81 +701,36 @@ int run_search(const flmr_corpus* c, flmr_workspace* ws, const void* d_q, int n_
     }
   }
 
-  const int rbq_total = (nq + 31) / 32;
+  std::vector<PassPlan> plan;
+  int group = 1;
+  plan_passes(n_queries, nq, &plan, &group);
+  if (!d_all_scores && nq > kRbMax * 32 && ws->acc_capacity < static_cast<int64_t>(group) * c->n_passages) {
+    if (ws->d_acc) cudaFree(ws->d_acc);
+    ws->d_acc = nullptr;
+    ws->acc_capacity = 0;
+    FLMR_CUDA(cudaMalloc(reinterpret_cast<void**>(&ws->d_acc),
+                         static_cast<size_t>(group) * c->n_passages * sizeof(float)));
+    ws->acc_capacity = static_cast<int64_t>(group) * c->n_passages;
+  }
   int rc;
-  if (rbq_total <= kRbMax) {
-    // whole queries resident: as many queries per corpus pass as fit kRbMax 32-row blocks
-    // ... spread evenly over the passes that takes (64 queries of one row block: 4 passes of 16 rather
-    // than 20+20+20+4, whose last pass would be HBM-bound while the others are tensor-bound)
-    const int qpp_max = std::min(kNqMax, kRbMax / rbq_total);
-    const int n_passes = (n_queries + qpp_max - 1) / qpp_max;
-    const int qpp = (n_queries + n_passes - 1) / n_passes;
-    for (int b0 = 0; b0 < n_queries; b0 += qpp) {
-      const int nqp = std::min(qpp, n_queries - b0);
-      const int n_mtiles = (nqp * rbq_total * 32 + kTileM - 1) / kTileM;
-      if ((rc = stage_queries(ws, d_q, b0, nqp, nq, 0, nq, rbq_total, n_mtiles, st))) return rc;
-      p.n_mtiles = n_mtiles;
-      p.nq_pass = nqp;
-      p.rbq = rbq_total;
-      p.acc_in = nullptr;
-      p.acc_out = d_all_scores ? d_all_scores + static_cast<int64_t>(b0) * c->n_passages : nullptr;
-      p.k = k;
-      if ((rc = launch_scan(c, ws, p, st))) return rc;
-      if (k > 0 &&
-          (rc = launch_merge_keys(c, ws, nqp, k, d_topk_scores + static_cast<int64_t>(b0) * k,
-                                  d_topk_pids + static_cast<int64_t>(b0) * k, st)))
-        return rc;
-    }
-  } else {
-    // queries longer than one pass holds: rows sliced over several corpus passes, partial scores carried
-    // through HBM (acc_in / acc_out).  Full slices take one pass per query; the TAIL slices of up to
-    // `group` queries share one pass (Nq = 832: 3 queries = 3 full passes + 1 tail pass instead of 6).
-    const int rows_per_slice = kRbMax * 32;
-    const int n_slices = (nq + rows_per_slice - 1) / rows_per_slice;
-    const int tail_row0 = (n_slices - 1) * rows_per_slice;
-    const int tail_rows = nq - tail_row0;
-    const int tail_rbq = (tail_rows + 31) / 32;
-    const int group = std::max(1, std::min({kNqMax, kRbMax / tail_rbq, n_queries}));
-    if (!d_all_scores && ws->acc_capacity < static_cast<int64_t>(group) * c->n_passages) {
-      if (ws->d_acc) cudaFree(ws->d_acc);
-      ws->d_acc = nullptr;
-      ws->acc_capacity = 0;
-      FLMR_CUDA(cudaMalloc(reinterpret_cast<void**>(&ws->d_acc),
-                           static_cast<size_t>(group) * c->n_passages * sizeof(float)));
-      ws->acc_capacity = static_cast<int64_t>(group) * c->n_passages;
-    }
-    for (int b0 = 0; b0 < n_queries; b0 += group) {
-      const int g = std::min(group, n_queries - b0);
-      float* acc = d_all_scores ? d_all_scores + static_cast<int64_t>(b0) * c->n_passages : ws->d_acc;
-      for (int b = 0; b < g; ++b) {                         // full slices, one query per pass
-        float* acc_b = acc + static_cast<int64_t>(b) * c->n_passages;
-        for (int s = 0; s + 1 < n_slices; ++s) {
-          if ((rc = stage_queries(ws, d_q, b0 + b, 1, nq, s * rows_per_slice, rows_per_slice, kRbMax,
-                                  kRbMax * 32 / kTileM, st)))
-            return rc;
-          p.n_mtiles = kRbMax * 32 / kTileM;
-          p.nq_pass = 1;
-          p.rbq = kRbMax;
-          p.acc_in = (s == 0) ? nullptr : acc_b;
-          p.acc_out = acc_b;
-          p.k = 0;
-          if ((rc = launch_scan(c, ws, p, st))) return rc;
-        }
-      }
-      // tail slices of the g queries together
-      const int n_mtiles = (g * tail_rbq * 32 + kTileM - 1) / kTileM;
-      if ((rc = stage_queries(ws, d_q, b0, g, nq, tail_row0, tail_rows, tail_rbq, n_mtiles, st))) return rc;
-      p.n_mtiles = n_mtiles;
-      p.nq_pass = g;
-      p.rbq = tail_rbq;
-      p.acc_in = acc;
-      p.acc_out = d_all_scores ? acc : nullptr;
-      p.k = k;
-      if ((rc = launch_scan(c, ws, p, st))) return rc;
-      if (k > 0 && (rc = launch_merge_keys(c, ws, g, k, d_topk_scores + static_cast<int64_t>(b0) * k,
-                                           d_topk_pids + static_cast<int64_t>(b0) * k, st)))
-        return rc;
-    }
+  for (const PassPlan& pp : plan) {
+    // partial / final scores of query (group_first + acc_slot + i) live in row i of `acc`
+    float* acc = d_all_scores
+                     ? d_all_scores + static_cast<int64_t>(pp.group_first + pp.acc_slot) * c->n_passages
+                     : (ws->d_acc ? ws->d_acc + static_cast<int64_t>(pp.acc_slot) * c->n_passages : nullptr);
+    if ((rc = stage_queries(ws, d_q, pp.q_first, pp.n_q, nq, pp.row0, pp.rows, pp.rbq, pp.n_mtiles, st)))
+      return rc;
+    p.n_mtiles = pp.n_mtiles;
+    p.nq_pass = pp.n_q;
+    p.rbq = pp.rbq;
+    p.acc_in = (pp.flags & kPassAccIn) ? acc : nullptr;
+    p.acc_out = ((pp.flags & kPassAccOut) || ((pp.flags & kPassFinal) && d_all_scores)) ? acc : nullptr;
+    p.k = (pp.flags & kPassFinal) ? k : 0;
+    if ((rc = launch_scan(c, ws, p, st))) return rc;
+    if ((pp.flags & kPassFinal) && k > 0 &&
+        (rc = launch_merge_keys(c, ws, pp.n_q, k, d_topk_scores + static_cast<int64_t>(pp.q_first) * k,
+                                d_topk_pids + static_cast<int64_t>(pp.q_first) * k, st)))
+      return rc;
   }
   return FLMR_OK;
 }
@@ -1183,6 +1190,24 @@ int flmr_debug_build_partition(const int32_t* h_doclens, int64_t n_passages, int
       return fail(FLMR_ERR_INVALID_ARG, "tile_capacity %lld < %zu tiles", (long long)tile_capacity, em.size());
     std::copy(em.begin(), em.end(), tile_end_mask);
     std::copy(fp.begin(), fp.end(), tile_first_pid);
+  }
+  return FLMR_OK;
+}
+
+int flmr_debug_plan_passes(int n_queries, int nq, int32_t* out_plan, int capacity, int* n_passes_out) {
+  if (n_queries < 0 || nq <= 0 || !n_passes_out) return fail(FLMR_ERR_INVALID_ARG, "bad argument");
+  std::vector<PassPlan> plan;
+  int group = 1;
+  plan_passes(n_queries, nq, &plan, &group);
+  *n_passes_out = static_cast<int>(plan.size());
+  if (out_plan) {
+    if (static_cast<int>(plan.size()) > capacity)
+      return fail(FLMR_ERR_INVALID_ARG, "capacity %d < %zu passes", capacity, plan.size());
+    for (size_t i = 0; i < plan.size(); ++i) {
+      const PassPlan& q = plan[i];
+      const int32_t row[8] = {q.q_first, q.n_q, q.row0, q.rows, q.rbq, q.n_mtiles, q.flags, q.group_first + q.acc_slot};
+      std::copy(row, row + 8, out_plan + i * 8);
+    }
   }
   return FLMR_OK;
 }

@@ -371,8 +371,8 @@ flmr_scan_kernel(const __grid_constant__ CUtensorMap tmap_d, const ScanParams p)
       tc_fence_after_sync();
       const uint64_t b_desc0 = make_kmajor_sw128_desc(smem_base + S::kOffD + s * kDTileBytes);
       const uint32_t a_first = static_cast<uint32_t>(t) * n_mtiles;
-#pragma unroll 1
       const bool rot = ((n_mtiles & t) & 1) != 0;  // odd tile, odd tile count: rotated order (see epilogue)
+#pragma unroll 1
       for (uint32_t a = a_first + ((a_first ^ iw) & 1u); a < a_first + n_mtiles; a += 2) {
         const uint32_t j = a - a_first;
         const uint32_t mt = rot ? (j == 0 ? static_cast<uint32_t>(n_mtiles) - 1u : j - 1u) : j;
@@ -457,8 +457,8 @@ flmr_scan_kernel(const __grid_constant__ CUtensorMap tmap_d, const ScanParams p)
       mbar_wait(bar_p_empty(buf), ((static_cast<uint32_t>(t) >> 1) & 1u) ^ 1u, p.status,
                 kDevTimeoutEpilogue);
       const uint32_t a_first = static_cast<uint32_t>(t) * n_mtiles;
-#pragma unroll 1
       const bool rot = ((n_mtiles & t) & 1) != 0;
+#pragma unroll 1
       for (uint32_t a = a_first + ((a_first ^ static_cast<uint32_t>(wg)) & 1u); a < a_first + n_mtiles;
            a += 2) {
         const int j = static_cast<int>(a - a_first);

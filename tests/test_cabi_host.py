@@ -128,3 +128,51 @@ def test_partition_invariants(seed, n, lo, hi, ctas):
     # token balance: no CTA holds more than the ideal share + one passage
     share = poff[-1] / nc
     assert np.all(np.diff(rb) <= share + plen.max() + 1)
+
+
+def _plan(n_queries, nq):
+    L = _cabi.lib()
+    n = C.c_int(0)
+    _cabi.check(L.flmr_debug_plan_passes(n_queries, nq, None, 0, C.byref(n)))
+    buf = np.zeros((max(n.value, 1), 8), dtype=np.int32)
+    _cabi.check(L.flmr_debug_plan_passes(n_queries, nq, buf.ctypes.data_as(C.c_void_p), n.value, C.byref(n)))
+    return buf[: n.value]
+
+
+@pytest.mark.parametrize("n_queries,nq", [(1, 32), (16, 32), (64, 32), (21, 32), (16, 320), (5, 320), (3, 45),
+                                           (7, 832), (1, 832), (3, 1500), (2, 1280), (40, 641), (0, 64), (13, 640)])
+def test_pass_plan_invariants(n_queries, nq):
+    """flmr_debug_plan_passes: every (query, row) is resident in exactly one pass, never more than 640 rows
+    or 20 queries per pass, partial scores are read only after they were written, each query is finalised
+    exactly once and last, and the number of passes is the minimum this scheme allows."""
+    plan = _plan(n_queries, nq)
+    ACC_IN, ACC_OUT, FINAL = 1, 2, 4
+    covered = np.zeros((n_queries, nq), dtype=np.int32)
+    touched = np.zeros(n_queries, dtype=bool)
+    finalised = np.zeros(n_queries, dtype=bool)
+    for q_first, n_q, row0, rows, rbq, n_mtiles, flags, acc_first in plan:
+        assert 1 <= n_q <= 20 and rbq == (rows + 31) // 32 and n_q * rbq <= 20
+        assert n_mtiles == (n_q * rbq * 32 + 127) // 128 and 1 <= n_mtiles <= 5
+        assert 0 <= row0 and row0 + rows <= nq and row0 % 32 == 0
+        qs = slice(q_first, q_first + n_q)
+        assert not finalised[qs].any()                        # nothing after the final pass of a query
+        assert bool(flags & ACC_IN) == bool(touched[qs].all()) and touched[qs].all() == touched[qs].any()
+        if not flags & FINAL:
+            assert flags & ACC_OUT                            # a non-final slice must store its partial scores
+        covered[qs, row0:row0 + rows] += 1
+        touched[qs] = True
+        if flags & FINAL:
+            finalised[qs] = True
+        assert acc_first == q_first                           # partial-score rows are indexed by query
+    assert (covered == 1).all() and finalised.all()
+    rbq_total = (nq + 31) // 32
+    if rbq_total <= 20:
+        per_pass = min(20, 20 // rbq_total)
+        assert len(plan) == -(-n_queries // per_pass)
+        sizes = [p[1] for p in plan]
+        assert not sizes or max(sizes) - min(sizes) <= per_pass - 1 and max(sizes) == -(-n_queries // len(plan))
+    else:
+        n_slices = -(-nq // 640)
+        tail_rbq = (nq - (n_slices - 1) * 640 + 31) // 32
+        group = max(1, min(20, 20 // tail_rbq, n_queries))
+        assert len(plan) == n_queries * (n_slices - 1) + -(-n_queries // group)
