@@ -176,3 +176,20 @@ def test_pass_plan_invariants(n_queries, nq):
         tail_rbq = (nq - (n_slices - 1) * 640 + 31) // 32
         group = max(1, min(20, 20 // tail_rbq, n_queries))
         assert len(plan) == n_queries * (n_slices - 1) + -(-n_queries // group)
+
+
+def test_pass_plan_random_shapes():
+    """Same invariants as above on a sweep of random (batch, query length) pairs."""
+    rng = np.random.default_rng(11)
+    for _ in range(60):
+        n_queries = int(rng.integers(0, 90))
+        nq = int(rng.integers(1, 2100))
+        plan = _plan(n_queries, nq)
+        covered = np.zeros((n_queries, nq), dtype=np.int32)
+        final = np.zeros(n_queries, dtype=np.int32)
+        for q_first, n_q, row0, rows, rbq, n_mtiles, flags, _acc in plan:
+            assert n_q * rbq <= 20 and n_q <= 20 and rows <= 640
+            covered[q_first:q_first + n_q, row0:row0 + rows] += 1
+            if flags & 4:
+                final[q_first:q_first + n_q] += 1
+        assert (covered == 1).all() and (final == 1).all(), (n_queries, nq)
