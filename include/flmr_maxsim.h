@@ -48,7 +48,7 @@
 extern "C" {
 #endif
 
-#define FLMR_ABI_VERSION 1
+#define FLMR_ABI_VERSION 2
 
 /* status codes */
 #define FLMR_OK 0
@@ -108,7 +108,11 @@ int flmr_corpus_create(const void* tokens, const int32_t* h_doclens, int64_t n_p
 int flmr_corpus_destroy(flmr_corpus_t* corpus);
 int flmr_corpus_info(const flmr_corpus_t* corpus, flmr_corpus_info_t* out);
 
-/* Scratch for searches on `corpus` with up to max_queries x max_nq query tokens per call. */
+/* Scratch for searches on `corpus`.  max_queries (>= 1) sizes the per-CTA candidate buffer: a call with more
+ * queries is processed in chunks of max_queries (each chunk: its scan passes + ONE merge launch).  max_nq
+ * (>= 1) is the longest query expected: if it exceeds the 640 rows one pass holds, the partial-score rows of
+ * row-sliced queries are allocated here instead of inside the first such search (longer queries still work,
+ * the buffer then grows on demand). */
 int flmr_workspace_create(const flmr_corpus_t* corpus, int max_queries, int max_nq,
                           flmr_workspace_t** out);
 int flmr_workspace_destroy(flmr_workspace_t* ws);
@@ -211,6 +215,23 @@ int flmr_maxsim_argmax(const void* d_q, int n_queries, int nq, const void* d_doc
 int flmr_maxsim_backward(const void* d_q, int n_queries, int nq, const void* d_docs, int n_docs, int nd,
                          const int32_t* d_argmax, const float* d_grad, float* d_dq, float* d_dd,
                          int device, void* stream);
+
+/*
+ * Block-diagonal ("aligned") form of the two calls above: query b meets only ITS docs_per_query documents,
+ * d_docs[b * docs_per_query .. (b + 1) * docs_per_query).  This is ColBERT.score(Q.repeat_interleave(nway), D,
+ * D_mask) (CB/modeling/colbert.py:71-73, 217-224; src/models/rag/rag_model_blip.py:430-435;
+ * src/executors/FLMR_executor.py:828-833) without materialising the repeated queries and without scoring the
+ * off-diagonal pairs.
+ *   d_docs  bf16 [n_queries * docs_per_query, nd, FLMR_DIM]    d_mask uint8 [n_queries * docs_per_query, nd]
+ *   d_argmax / d_rowmax [n_queries, docs_per_query, nq]        d_grad fp32 [n_queries, docs_per_query]
+ *   d_dq fp32 [n_queries, nq, FLMR_DIM]                        d_dd fp32 [n_queries * docs_per_query, nd, FLMR_DIM]
+ */
+int flmr_maxsim_argmax_grouped(const void* d_q, int n_queries, int nq, const void* d_docs,
+                               const uint8_t* d_mask, int docs_per_query, int nd, int32_t* d_argmax,
+                               float* d_rowmax, int device, void* stream);
+int flmr_maxsim_backward_grouped(const void* d_q, int n_queries, int nq, const void* d_docs,
+                                 int docs_per_query, int nd, const int32_t* d_argmax, const float* d_grad,
+                                 float* d_dq, float* d_dd, int device, void* stream);
 
 /* Test infrastructure: plain SIMT fp32 MaxSim of every passage (same contract as
  * flmr_maxsim_scores), independent of the tensor-core kernel. */

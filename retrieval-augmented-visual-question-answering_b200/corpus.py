@@ -94,15 +94,26 @@ class FlatCorpus:
             all_doclens = np.concatenate([np.load(os.path.join(path, "doclens.%d.npy" % c))
                                           for c in range(meta["num_chunks"])])
         p0, p1 = shard_ranges(all_doclens, world_size)[rank]
+        if p0 == p1:
+            return None          # more ranks than passages: this rank holds nothing (Searcher copes)
         tokens, doclens, _ = load_flat_index(path, passage_range=(p0, p1))
         return cls(tokens, doclens, device=device, pid_base=p0)
 
     @classmethod
-    def from_plaid(cls, path: str, device=None) -> "FlatCorpus":
-        """Decode a reference PLAID index directory on the GPU (plaid.py) and keep it resident."""
-        from .plaid import plaid_to_flat
-        tokens, doclens = plaid_to_flat(path, device)
-        return cls(tokens, doclens, device=tokens.device)
+    def from_plaid(cls, path: str, device=None, rank: int = 0, world_size: int = 1) -> "FlatCorpus":
+        """Decode a reference PLAID index directory on the GPU (plaid.py) and keep it resident — with
+        world_size > 1 only this rank's contiguous, token-balanced passage shard."""
+        from .plaid import plaid_to_flat, read_plaid_doclens, read_plaid_metadata
+        from .sharded import shard_ranges
+        if world_size == 1:
+            tokens, doclens = plaid_to_flat(path, device)
+            return cls(tokens, doclens, device=tokens.device)
+        all_doclens = np.concatenate(read_plaid_doclens(path, read_plaid_metadata(path)["num_chunks"]))
+        p0, p1 = shard_ranges(all_doclens, world_size)[rank]
+        if p0 == p1:
+            return None
+        tokens, doclens = plaid_to_flat(path, device, passage_range=(p0, p1))
+        return cls(tokens, doclens, device=tokens.device, pid_base=p0)
 
     # -- properties ---------------------------------------------------------------------------
     @property

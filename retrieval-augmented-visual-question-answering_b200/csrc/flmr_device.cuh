@@ -71,7 +71,9 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 // `status` receives `code` before the trap so the host can say which role starved.  The spinning
 // path is kept out of line so the hot loops stay small (instruction-cache footprint).
 __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity, int* status, int code) {
-  constexpr uint64_t timeout_ns = 4000000000ull;   // 4 s of polling = a protocol bug, not a slow wait
+  // 20 s of polling = a protocol bug, not a slow wait (time slicing, a sanitizer or a debugger can stretch a
+  // legitimate wait to seconds; the longest real wait of a scan is one tile, microseconds)
+  constexpr uint64_t timeout_ns = 20000000000ull;
   uint32_t spins = 0;
   uint64_t t0 = 0;
   while (!mbar_try_wait(bar, parity)) {

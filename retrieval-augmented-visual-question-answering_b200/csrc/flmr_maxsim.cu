@@ -203,7 +203,10 @@ __global__ void flmr_plaid_decode_kernel(const int32_t* __restrict__ codes,
   for (int64_t t = warp0; t < n_tokens; t += n_warps) {
     const int32_t code = codes[t];
     if (code < 0 || code >= n_centroids) {    // corrupt index: flag, never read out of bounds
-      if (lane == 0) *bad_code = 1;
+      if (lane == 0) {
+        *reinterpret_cast<volatile int*>(bad_code) = 1;
+        __threadfence_system();
+      }
       continue;
     }
     const float4 c = __ldg(reinterpret_cast<const float4*>(centroids + static_cast<int64_t>(code) * kDim) + lane);
@@ -485,11 +488,12 @@ struct flmr_workspace {
   int device = 0;
   int max_queries = 0, max_nq = 0;
   __nv_bfloat16* d_qpad = nullptr;     // [kMtMax*128, 128] staged (zero-padded) queries of one pass
-  uint64_t* d_cand_keys = nullptr;     // [n_ctas][kNqMax][kMaxK]
+  uint64_t* d_cand_keys = nullptr;     // [n_ctas][max_queries][k] candidate keys of one call chunk
   float* d_acc = nullptr;              // [group][n_passages] lazily allocated (row-sliced queries)
   int64_t acc_capacity = 0;            // floats allocated at d_acc
   int* h_status = nullptr;             // pinned + mapped: readable by the host even after a device trap
   int* d_status = nullptr;             // device alias of h_status
+  int dbg_mode = 0, dbg_lane_rbq = 4;  // -DFLMR_DEBUG builds: FLMR_DEBUG_MODE / FLMR_LANE_RBQ, read once at creation
 };
 
 namespace {
@@ -607,7 +611,11 @@ void plan_passes(int n_queries, int nq, std::vector<PassPlan>* out, int* group_o
 int launch_scan(const flmr_corpus* c, flmr_workspace* ws, const ScanParams& p, cudaStream_t st) {
   // product instantiation unless a timing experiment / timestamp mode was requested
   // (both instantiations got their dynamic-shared-memory limit raised in flmr_corpus_create)
+#ifdef FLMR_DEBUG
   auto kern = p.debug_mode ? flmr_scan_kernel<true> : flmr_scan_kernel<false>;
+#else
+  auto kern = flmr_scan_kernel<false>;
+#endif
   EventPair ev{};
   if (g_profiling) {
     FLMR_CUDA(cudaEventCreate(&ev.a));
@@ -639,6 +647,7 @@ int stage_queries(flmr_workspace* ws, const void* d_q, int64_t q_first, int nq_p
   return FLMR_OK;
 }
 
+// One launch merges the per-CTA candidate lists of ALL queries of a call (block b = query b).
 int launch_merge_keys(const flmr_corpus* c, flmr_workspace* ws, int nq_pass, int k,
                       float* d_out_scores, int64_t* d_out_pids, cudaStream_t st) {
   if (static_cast<int64_t>(c->n_ctas) * k > kMergeThreads * kMergePer)
@@ -649,6 +658,17 @@ int launch_merge_keys(const flmr_corpus* c, flmr_workspace* ws, int nq_pass, int
                                                        d_out_pids);
   FLMR_CUDA(cudaGetLastError());
   ++g_launches;
+  return FLMR_OK;
+}
+
+// Partial-score rows of row-sliced (Nq > 640) queries: grown on demand, never shrunk.
+int ensure_acc(flmr_workspace* ws, int64_t floats) {
+  if (ws->acc_capacity >= floats) return FLMR_OK;
+  if (ws->d_acc) cudaFree(ws->d_acc);
+  ws->d_acc = nullptr;
+  ws->acc_capacity = 0;
+  FLMR_CUDA(cudaMalloc(reinterpret_cast<void**>(&ws->d_acc), static_cast<size_t>(floats) * sizeof(float)));
+  ws->acc_capacity = floats;
   return FLMR_OK;
 }
 
@@ -680,8 +700,9 @@ int run_search(const flmr_corpus* c, flmr_workspace* ws, const void* d_q, int n_
   p.q_pad = reinterpret_cast<const uint4*>(ws->d_qpad);
   p.status = ws->d_status;
   p.lane_mode_max_rbq = 4;   // measured (profiles/r01_debug_mode_probes.log): lane-per-query wins up to 4 row blocks per query
-  if (const char* e = getenv("FLMR_LANE_RBQ")) p.lane_mode_max_rbq = atoi(e);
-  if (const char* e = getenv("FLMR_DEBUG_MODE")) p.debug_mode = atoi(e);
+#ifdef FLMR_DEBUG   // timing experiments exist only in -DFLMR_DEBUG builds (tools/); the release library has no env hooks
+  p.lane_mode_max_rbq = ws->dbg_lane_rbq;
+  p.debug_mode = ws->dbg_mode;
   if (p.debug_mode == 6) {  // timestamps of CTA 0's accumulator hand-offs, dumped by the caller
     static long long* d_ts = nullptr;
     if (!d_ts) {
@@ -700,36 +721,39 @@ int run_search(const flmr_corpus* c, flmr_workspace* ws, const void* d_q, int n_
       }
     }
   }
+#endif
 
+  // a call is processed in chunks of at most ws->max_queries queries (the candidate buffer's capacity);
+  // within a chunk: every pass's scan, then ONE merge launch over all of the chunk's queries
   std::vector<PassPlan> plan;
-  int group = 1;
-  plan_passes(n_queries, nq, &plan, &group);
-  if (!d_all_scores && nq > kRbMax * 32 && ws->acc_capacity < static_cast<int64_t>(group) * c->n_passages) {
-    if (ws->d_acc) cudaFree(ws->d_acc);
-    ws->d_acc = nullptr;
-    ws->acc_capacity = 0;
-    FLMR_CUDA(cudaMalloc(reinterpret_cast<void**>(&ws->d_acc),
-                         static_cast<size_t>(group) * c->n_passages * sizeof(float)));
-    ws->acc_capacity = static_cast<int64_t>(group) * c->n_passages;
-  }
   int rc;
-  for (const PassPlan& pp : plan) {
-    // partial / final scores of query (group_first + acc_slot + i) live in row i of `acc`
-    float* acc = d_all_scores
-                     ? d_all_scores + static_cast<int64_t>(pp.group_first + pp.acc_slot) * c->n_passages
-                     : (ws->d_acc ? ws->d_acc + static_cast<int64_t>(pp.acc_slot) * c->n_passages : nullptr);
-    if ((rc = stage_queries(ws, d_q, pp.q_first, pp.n_q, nq, pp.row0, pp.rows, pp.rbq, pp.n_mtiles, st)))
+  for (int c0 = 0; c0 < n_queries; c0 += ws->max_queries) {
+    const int nqc = std::min(ws->max_queries, n_queries - c0);
+    const __nv_bfloat16* d_qc = static_cast<const __nv_bfloat16*>(d_q) + static_cast<int64_t>(c0) * nq * kDim;
+    float* d_all_c = d_all_scores ? d_all_scores + static_cast<int64_t>(c0) * c->n_passages : nullptr;
+    int group = 1;
+    plan_passes(nqc, nq, &plan, &group);
+    if (!d_all_c && nq > kRbMax * 32 && (rc = ensure_acc(ws, static_cast<int64_t>(group) * c->n_passages)))
       return rc;
-    p.n_mtiles = pp.n_mtiles;
-    p.nq_pass = pp.n_q;
-    p.rbq = pp.rbq;
-    p.acc_in = (pp.flags & kPassAccIn) ? acc : nullptr;
-    p.acc_out = ((pp.flags & kPassAccOut) || ((pp.flags & kPassFinal) && d_all_scores)) ? acc : nullptr;
-    p.k = (pp.flags & kPassFinal) ? k : 0;
-    if ((rc = launch_scan(c, ws, p, st))) return rc;
-    if ((pp.flags & kPassFinal) && k > 0 &&
-        (rc = launch_merge_keys(c, ws, pp.n_q, k, d_topk_scores + static_cast<int64_t>(pp.q_first) * k,
-                                d_topk_pids + static_cast<int64_t>(pp.q_first) * k, st)))
+    p.cand_q_stride = nqc;
+    for (const PassPlan& pp : plan) {
+      // partial / final scores of query (group_first + acc_slot + i) live in row i of `acc`
+      float* acc = d_all_c
+                       ? d_all_c + static_cast<int64_t>(pp.group_first + pp.acc_slot) * c->n_passages
+                       : (ws->d_acc ? ws->d_acc + static_cast<int64_t>(pp.acc_slot) * c->n_passages : nullptr);
+      if ((rc = stage_queries(ws, d_qc, pp.q_first, pp.n_q, nq, pp.row0, pp.rows, pp.rbq, pp.n_mtiles, st)))
+        return rc;
+      p.n_mtiles = pp.n_mtiles;
+      p.nq_pass = pp.n_q;
+      p.rbq = pp.rbq;
+      p.acc_in = (pp.flags & kPassAccIn) ? acc : nullptr;
+      p.acc_out = ((pp.flags & kPassAccOut) || ((pp.flags & kPassFinal) && d_all_c)) ? acc : nullptr;
+      p.k = (pp.flags & kPassFinal) ? k : 0;
+      p.cand_q_first = pp.q_first;
+      if ((rc = launch_scan(c, ws, p, st))) return rc;
+    }
+    if (k > 0 && (rc = launch_merge_keys(c, ws, nqc, k, d_topk_scores + static_cast<int64_t>(c0) * k,
+                                         d_topk_pids + static_cast<int64_t>(c0) * k, st)))
       return rc;
   }
   return FLMR_OK;
@@ -872,7 +896,9 @@ int flmr_corpus_create(const void* tokens, const int32_t* h_doclens, int64_t n_p
 
   // --- partition + tile metadata ---
   int n_ctas = prop.multiProcessorCount;
+#ifdef FLMR_DEBUG
   if (const char* e = getenv("FLMR_NUM_CTAS")) n_ctas = std::max(1, atoi(e));
+#endif
   n_ctas = static_cast<int>(std::min<int64_t>(n_ctas, n_passages));
   c->n_ctas = n_ctas;
   {
@@ -891,8 +917,12 @@ int flmr_corpus_create(const void* tokens, const int32_t* h_doclens, int64_t n_p
   {  // per-device function attribute, set here (idempotent) rather than at launch time
     cudaError_t e1 = cudaFuncSetAttribute(flmr_scan_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           ScanSmem::kBytes);
+#ifdef FLMR_DEBUG
     cudaError_t e2 = cudaFuncSetAttribute(flmr_scan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           ScanSmem::kBytes);
+#else
+    cudaError_t e2 = cudaSuccess;
+#endif
     if (e1 != cudaSuccess || e2 != cudaSuccess)
       return bail(fail(FLMR_ERR_CUDA, "cannot raise the dynamic shared memory limit to %d bytes: %s",
                        ScanSmem::kBytes, cudaGetErrorString(e1 != cudaSuccess ? e1 : e2)));
@@ -934,6 +964,8 @@ int flmr_workspace_create(const flmr_corpus_t* c, int max_queries, int max_nq,
                           flmr_workspace_t** out) {
   if (!c || !out) return fail(FLMR_ERR_INVALID_ARG, "null argument");
   *out = nullptr;
+  if (max_queries < 1 || max_nq < 1)
+    return fail(FLMR_ERR_INVALID_ARG, "max_queries=%d / max_nq=%d must be >= 1", max_queries, max_nq);
   DeviceGuard guard(c->device);
   if (!guard.ok) return fail(FLMR_ERR_CUDA, "cudaSetDevice(%d) failed", c->device);
   flmr_workspace* ws = new (std::nothrow) flmr_workspace();
@@ -951,11 +983,21 @@ int flmr_workspace_create(const flmr_corpus_t* c, int max_queries, int max_nq,
   if ((e = cudaMalloc(reinterpret_cast<void**>(&ws->d_qpad), qbytes)) != cudaSuccess ||
       (e = cudaMemset(ws->d_qpad, 0, qbytes)) != cudaSuccess ||
       (e = cudaMalloc(reinterpret_cast<void**>(&ws->d_cand_keys),
-                      static_cast<size_t>(c->n_ctas) * kNqMax * kMaxK * 8)) != cudaSuccess ||
+                      static_cast<size_t>(c->n_ctas) * max_queries * kMaxK * 8)) != cudaSuccess ||
       (e = cudaHostAlloc(reinterpret_cast<void**>(&ws->h_status), sizeof(int), cudaHostAllocMapped)) != cudaSuccess ||
       (e = cudaHostGetDevicePointer(reinterpret_cast<void**>(&ws->d_status), ws->h_status, 0)) != cudaSuccess)
     return bail(fail(FLMR_ERR_CUDA, "workspace allocation failed: %s", cudaGetErrorString(e)));
   *ws->h_status = 0;
+  if (max_nq > kRbMax * 32) {   // row-sliced queries expected: size their partial-score rows now
+    std::vector<PassPlan> plan;
+    int group = 1;
+    plan_passes(max_queries, max_nq, &plan, &group);
+    if (int rc = ensure_acc(ws, static_cast<int64_t>(group) * c->n_passages)) return bail(rc);
+  }
+#ifdef FLMR_DEBUG
+  if (const char* e = getenv("FLMR_DEBUG_MODE")) ws->dbg_mode = atoi(e);
+  if (const char* e = getenv("FLMR_LANE_RBQ")) ws->dbg_lane_rbq = atoi(e);
+#endif
   *out = ws;
   return FLMR_OK;
 }
@@ -1027,9 +1069,13 @@ int flmr_plaid_decode(const int32_t* d_codes, const uint8_t* d_residuals, int64_
   DeviceGuard guard(device);
   if (!guard.ok) return fail(FLMR_ERR_CUDA, "cudaSetDevice(%d) failed", device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // "a code was out of range" flag: one pinned + mapped word per host thread, reused by every call
+  thread_local int* h_bad = nullptr;
+  if (!h_bad) FLMR_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&h_bad), sizeof(int), cudaHostAllocMapped | cudaHostAllocPortable));
   int* d_bad = nullptr;
-  FLMR_CUDA(cudaMalloc(reinterpret_cast<void**>(&d_bad), sizeof(int)));
-  cudaError_t e = cudaMemsetAsync(d_bad, 0, sizeof(int), st);
+  FLMR_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&d_bad), h_bad, 0));
+  *reinterpret_cast<volatile int*>(h_bad) = 0;
+  cudaError_t e = cudaSuccess;
   const int threads = 256;
   const int64_t want = (n_tokens * 32 + threads - 1) / threads;
   const int blocks = static_cast<int>(std::min<int64_t>(want, 148 * 16));
@@ -1040,10 +1086,8 @@ int flmr_plaid_decode(const int32_t* d_codes, const uint8_t* d_residuals, int64_
     ++g_launches;
     e = cudaGetLastError();
   }
-  int bad = 0;
-  if (e == cudaSuccess) e = cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, st);
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-  cudaFree(d_bad);
+  const int bad = *reinterpret_cast<volatile int*>(h_bad);
   if (e != cudaSuccess) return fail(FLMR_ERR_CUDA, "plaid decode failed: %s", cudaGetErrorString(e));
   if (bad) return fail(FLMR_ERR_INVALID_ARG, "a centroid code is outside [0, %lld)", (long long)n_centroids);
   return FLMR_OK;
@@ -1083,68 +1127,104 @@ int flmr_corpus_gather(const flmr_corpus_t* c, const int64_t* d_pids, int64_t n_
   return FLMR_OK;
 }
 
-int flmr_maxsim_argmax(const void* d_q, int n_queries, int nq, const void* d_docs,
-                       const uint8_t* d_mask, int n_docs, int nd, int32_t* d_argmax, float* d_rowmax,
-                       int device, void* stream) {
+// n_per documents per query; stride_b = 0: all queries meet documents [0, n_per) (all pairs),
+// stride_b = n_per: query b meets documents [b * n_per, (b + 1) * n_per) (block diagonal).
+static int argmax_impl(const void* d_q, int n_queries, int nq, const void* d_docs, const uint8_t* d_mask,
+                       int n_per, int stride_b, int nd, int32_t* d_argmax, float* d_rowmax, int device,
+                       void* stream) {
   if (!d_q || !d_docs || !d_mask || !d_argmax) return fail(FLMR_ERR_INVALID_ARG, "null pointer");
-  if (n_queries < 0 || n_docs < 0 || nq <= 0 || nd <= 0)
-    return fail(FLMR_ERR_INVALID_ARG, "bad shape n_queries=%d nq=%d n_docs=%d nd=%d", n_queries, nq, n_docs, nd);
-  if (n_queries > 65535 || n_docs > 65535)
+  if (n_queries < 0 || n_per < 0 || nq <= 0 || nd <= 0)
+    return fail(FLMR_ERR_INVALID_ARG, "bad shape n_queries=%d nq=%d n_docs=%d nd=%d", n_queries, nq, n_per, nd);
+  if (n_queries > 65535 || n_per > 65535)
     return fail(FLMR_ERR_UNSUPPORTED, "n_queries / n_docs above 65535 (training-sized batches only)");
-  if (n_queries == 0 || n_docs == 0) return FLMR_OK;
+  if (n_queries == 0 || n_per == 0) return FLMR_OK;
   DeviceGuard guard(device);
   if (!guard.ok) return fail(FLMR_ERR_CUDA, "cudaSetDevice(%d) failed", device);
-  dim3 grid(static_cast<unsigned>((nq + kArgTile - 1) / kArgTile), static_cast<unsigned>(n_docs),
+  dim3 grid(static_cast<unsigned>((nq + kArgTile - 1) / kArgTile), static_cast<unsigned>(n_per),
             static_cast<unsigned>(n_queries));
-  // warp-MMA kernel by default; FLMR_ARGMAX_SIMT=1 selects the plain-FMA twin (cross-check / A-B timing)
+#ifdef FLMR_DEBUG
+  // debug builds: FLMR_ARGMAX_SIMT=1 selects the plain-FMA twin (cross-check / A-B timing)
   const char* simt = getenv("FLMR_ARGMAX_SIMT");
-  if (simt && atoi(simt))
+  if (simt && atoi(simt)) {
     flmr_argmax_kernel<<<grid, kArgThreads, 0, static_cast<cudaStream_t>(stream)>>>(
         static_cast<const __nv_bfloat16*>(d_q), static_cast<const __nv_bfloat16*>(d_docs), d_mask, nq, nd,
-        n_docs, d_argmax, d_rowmax);
-  else
-    flmr_argmax_mma_kernel<<<grid, kMmaThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-        static_cast<const __nv_bfloat16*>(d_q), static_cast<const __nv_bfloat16*>(d_docs), d_mask, nq, nd,
-        n_docs, d_argmax, d_rowmax);
+        n_per, stride_b, d_argmax, d_rowmax);
+    FLMR_CUDA(cudaGetLastError());
+    ++g_launches;
+    return FLMR_OK;
+  }
+#endif
+  flmr_argmax_mma_kernel<<<grid, kMmaThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(d_q), static_cast<const __nv_bfloat16*>(d_docs), d_mask, nq, nd,
+      n_per, stride_b, d_argmax, d_rowmax);
   FLMR_CUDA(cudaGetLastError());
   ++g_launches;
   return FLMR_OK;
 }
 
-int flmr_maxsim_backward(const void* d_q, int n_queries, int nq, const void* d_docs, int n_docs, int nd,
-                         const int32_t* d_argmax, const float* d_grad, float* d_dq, float* d_dd,
+static int backward_impl(const void* d_q, int n_queries, int nq, const void* d_docs, int n_per, int stride_b,
+                         int nd, const int32_t* d_argmax, const float* d_grad, float* d_dq, float* d_dd,
                          int device, void* stream) {
   if (!d_q || !d_docs || !d_argmax || !d_grad) return fail(FLMR_ERR_INVALID_ARG, "null pointer");
-  if (n_queries < 0 || n_docs < 0 || nq <= 0 || nd <= 0)
-    return fail(FLMR_ERR_INVALID_ARG, "bad shape n_queries=%d nq=%d n_docs=%d nd=%d", n_queries, nq, n_docs, nd);
+  if (n_queries < 0 || n_per < 0 || nq <= 0 || nd <= 0)
+    return fail(FLMR_ERR_INVALID_ARG, "bad shape n_queries=%d nq=%d n_docs=%d nd=%d", n_queries, nq, n_per, nd);
   DeviceGuard guard(device);
   if (!guard.ok) return fail(FLMR_ERR_CUDA, "cudaSetDevice(%d) failed", device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int threads = 256;
+  const int64_t n_docs_total = stride_b ? static_cast<int64_t>(n_queries) * n_per : n_per;
   if (d_dq && n_queries > 0) {
     const int64_t warps = static_cast<int64_t>(n_queries) * nq;
-    if (n_docs == 0) {
+    if (n_per == 0) {
       FLMR_CUDA(cudaMemsetAsync(d_dq, 0, static_cast<size_t>(warps) * kDim * sizeof(float), st));
     } else {
       flmr_bwd_dq_kernel<<<static_cast<unsigned>((warps * 32 + threads - 1) / threads), threads, 0, st>>>(
-          static_cast<const __nv_bfloat16*>(d_docs), d_argmax, d_grad, n_queries, nq, n_docs, nd, d_dq);
+          static_cast<const __nv_bfloat16*>(d_docs), d_argmax, d_grad, n_queries, nq, n_per, nd, stride_b, d_dq);
       FLMR_CUDA(cudaGetLastError());
       ++g_launches;
     }
   }
-  if (d_dd && n_docs > 0) {
-    FLMR_CUDA(cudaMemsetAsync(d_dd, 0, static_cast<size_t>(n_docs) * nd * kDim * sizeof(float), st));
-    const int64_t warps = static_cast<int64_t>(n_queries) * n_docs * nq;
+  if (d_dd && n_docs_total > 0) {
+    FLMR_CUDA(cudaMemsetAsync(d_dd, 0, static_cast<size_t>(n_docs_total) * nd * kDim * sizeof(float), st));
+    const int64_t warps = static_cast<int64_t>(n_queries) * n_per * nq;
     if (warps > 0) {
       if ((warps * 32 + threads - 1) / threads > 0x7fffffffll)
         return fail(FLMR_ERR_UNSUPPORTED, "backward grid too large (%lld warps)", (long long)warps);
       flmr_bwd_dd_kernel<<<static_cast<unsigned>((warps * 32 + threads - 1) / threads), threads, 0, st>>>(
-          static_cast<const __nv_bfloat16*>(d_q), d_argmax, d_grad, n_queries, nq, n_docs, nd, d_dd);
+          static_cast<const __nv_bfloat16*>(d_q), d_argmax, d_grad, n_queries, nq, n_per, nd, stride_b, d_dd);
       FLMR_CUDA(cudaGetLastError());
       ++g_launches;
     }
   }
   return FLMR_OK;
+}
+
+int flmr_maxsim_argmax(const void* d_q, int n_queries, int nq, const void* d_docs,
+                       const uint8_t* d_mask, int n_docs, int nd, int32_t* d_argmax, float* d_rowmax,
+                       int device, void* stream) {
+  return argmax_impl(d_q, n_queries, nq, d_docs, d_mask, n_docs, 0, nd, d_argmax, d_rowmax, device, stream);
+}
+
+int flmr_maxsim_backward(const void* d_q, int n_queries, int nq, const void* d_docs, int n_docs, int nd,
+                         const int32_t* d_argmax, const float* d_grad, float* d_dq, float* d_dd,
+                         int device, void* stream) {
+  return backward_impl(d_q, n_queries, nq, d_docs, n_docs, 0, nd, d_argmax, d_grad, d_dq, d_dd, device, stream);
+}
+
+int flmr_maxsim_argmax_grouped(const void* d_q, int n_queries, int nq, const void* d_docs,
+                               const uint8_t* d_mask, int docs_per_query, int nd, int32_t* d_argmax,
+                               float* d_rowmax, int device, void* stream) {
+  if (docs_per_query < 1) return fail(FLMR_ERR_INVALID_ARG, "docs_per_query=%d must be >= 1", docs_per_query);
+  return argmax_impl(d_q, n_queries, nq, d_docs, d_mask, docs_per_query, docs_per_query, nd, d_argmax, d_rowmax,
+                     device, stream);
+}
+
+int flmr_maxsim_backward_grouped(const void* d_q, int n_queries, int nq, const void* d_docs,
+                                 int docs_per_query, int nd, const int32_t* d_argmax, const float* d_grad,
+                                 float* d_dq, float* d_dd, int device, void* stream) {
+  if (docs_per_query < 1) return fail(FLMR_ERR_INVALID_ARG, "docs_per_query=%d must be >= 1", docs_per_query);
+  return backward_impl(d_q, n_queries, nq, d_docs, docs_per_query, docs_per_query, nd, d_argmax, d_grad, d_dq,
+                       d_dd, device, stream);
 }
 
 int flmr_debug_maxsim_scores_simt(const flmr_corpus_t* c, const void* d_q, int n_queries, int nq,

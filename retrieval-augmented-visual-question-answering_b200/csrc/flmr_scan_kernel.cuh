@@ -94,7 +94,9 @@ struct ScanParams {
   int64_t n_passages;
   // fused top-k
   int32_t k;                       // 0 = disabled
-  uint64_t* cand_keys;             // [n_ctas][nq_pass][k]  (ordered score << 32 | ~local pid)
+  uint64_t* cand_keys;             // [n_ctas][cand_q_stride][k]  (ordered score << 32 | ~local pid)
+  int32_t cand_q_stride;           // queries of the whole call chunk (one merge launch serves them all)
+  int32_t cand_q_first;            // index of this pass's first query inside the chunk
   // diagnostics
   int32_t debug_mode;              // 0 = product.  Timing-only experiments (results are garbage):
                                    // 1 = epilogue releases accumulators unread, 2 = TMEM reads but no
@@ -631,7 +633,7 @@ flmr_scan_kernel(const __grid_constant__ CUtensorMap tmap_d, const ScanParams p)
     if (p.k > 0) {
       __syncwarp();
       for (int b = rw; b < p.nq_pass; b += kRedWarps) {
-        uint64_t* dst = p.cand_keys + (static_cast<int64_t>(cta) * p.nq_pass + b) * p.k;
+        uint64_t* dst = p.cand_keys + (static_cast<int64_t>(cta) * p.cand_q_stride + p.cand_q_first + b) * p.k;
         for (int i = lane; i < p.k; i += 32) dst[i] = keys[b * kMaxK + i];
       }
     }

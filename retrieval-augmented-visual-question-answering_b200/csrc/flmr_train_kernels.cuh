@@ -34,17 +34,22 @@ __device__ __forceinline__ void bf16x4_to_float(uint2 v, float* f) {
 // arg[b, p, i] = argmax_{j : mask[p, j]} <Q[b, i, :], D[p, j, :]>   (lowest j on ties; -1 if p has no
 // unmasked token); rowmax[b, p, i] = that maximum (optional: summed over i it is the MaxSim score, which
 // makes this kernel the whole forward of a training-sized batch).  grid = (ceil(Nq / 64), n, B), block = 256.
+// Query b meets the n documents [b * stride_b, b * stride_b + n): stride_b = 0 is the all-pairs form
+// (every query against the same n documents), stride_b = n the block-diagonal one (query b against ITS n
+// documents: the aligned `score(Q.repeat_interleave(n), D)` of colbert.py:71 / rag_model_blip.py:433 /
+// FLMR_executor.py:828 without scoring the off-diagonal pairs).
 __global__ void __launch_bounds__(kArgThreads)
 flmr_argmax_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ d,
-                   const uint8_t* __restrict__ mask, int nq, int nd, int n, int32_t* __restrict__ arg,
-                   float* __restrict__ rowmax) {
+                   const uint8_t* __restrict__ mask, int nq, int nd, int n, int stride_b,
+                   int32_t* __restrict__ arg, float* __restrict__ rowmax) {
   __shared__ __align__(16) __nv_bfloat16 qs[kArgTile * kArgStride];
   __shared__ __align__(16) __nv_bfloat16 ds[kArgTile * kArgStride];
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   const int i0 = blockIdx.x * kArgTile, p = blockIdx.y, b = blockIdx.z;
+  const int64_t pg = static_cast<int64_t>(b) * stride_b + p;   // document row (stride_b = 0: all pairs)
   const __nv_bfloat16* qb = q + (static_cast<int64_t>(b) * nq + i0) * 128;
-  const __nv_bfloat16* db = d + static_cast<int64_t>(p) * nd * 128;
-  const uint8_t* mp = mask + static_cast<int64_t>(p) * nd;
+  const __nv_bfloat16* db = d + pg * nd * 128;
+  const uint8_t* mp = mask + pg * nd;
 
   // stage the query tile once (rows past Nq read as zero; their results are never stored)
   for (int t = tid; t < kArgTile * 32; t += kArgThreads) {
@@ -149,16 +154,17 @@ __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a
 
 __global__ void __launch_bounds__(kMmaThreads)
 flmr_argmax_mma_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ d,
-                       const uint8_t* __restrict__ mask, int nq, int nd, int n, int32_t* __restrict__ arg,
-                       float* __restrict__ rowmax) {
+                       const uint8_t* __restrict__ mask, int nq, int nd, int n, int stride_b,
+                       int32_t* __restrict__ arg, float* __restrict__ rowmax) {
   __shared__ __align__(16) __nv_bfloat16 qs[kArgTile * kMmaStride];
   __shared__ __align__(16) __nv_bfloat16 ds[kArgTile * kMmaStride];
   __shared__ uint8_t ms[kArgTile];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int i0 = blockIdx.x * kArgTile, p = blockIdx.y, b = blockIdx.z;
+  const int64_t pg = static_cast<int64_t>(b) * stride_b + p;   // document row (stride_b = 0: all pairs)
   const __nv_bfloat16* qb = q + (static_cast<int64_t>(b) * nq + i0) * 128;
-  const __nv_bfloat16* db = d + static_cast<int64_t>(p) * nd * 128;
-  const uint8_t* mp = mask + static_cast<int64_t>(p) * nd;
+  const __nv_bfloat16* db = d + pg * nd * 128;
+  const uint8_t* mp = mask + pg * nd;
 
   for (int t = tid; t < kArgTile * 16; t += kMmaThreads) {     // 16 uint4 (8 bf16) per row
     const int r = t >> 4, c = t & 15;
@@ -244,7 +250,7 @@ flmr_argmax_mma_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16*
 // dQ[b, i, :] = sum_p g[b, p] * D[p, arg[b, p, i], :].  One warp per (b, i), 4 dims per lane.
 __global__ void flmr_bwd_dq_kernel(const __nv_bfloat16* __restrict__ d, const int32_t* __restrict__ arg,
                                    const float* __restrict__ g, int B, int nq, int n, int nd,
-                                   float* __restrict__ dq) {
+                                   int stride_b, float* __restrict__ dq) {
   const int64_t w = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (w >= static_cast<int64_t>(B) * nq) return;
@@ -255,7 +261,8 @@ __global__ void flmr_bwd_dq_kernel(const __nv_bfloat16* __restrict__ d, const in
     const float gp = g[static_cast<int64_t>(b) * n + p];
     if (j < 0) continue;
     float f[4];
-    bf16x4_to_float(*reinterpret_cast<const uint2*>(d + (static_cast<int64_t>(p) * nd + j) * 128 + lane * 4), f);
+    bf16x4_to_float(*reinterpret_cast<const uint2*>(
+                        d + ((static_cast<int64_t>(b) * stride_b + p) * nd + j) * 128 + lane * 4), f);
 #pragma unroll
     for (int e = 0; e < 4; ++e) acc[e] = fmaf(gp, f[e], acc[e]);
   }
@@ -266,7 +273,7 @@ __global__ void flmr_bwd_dq_kernel(const __nv_bfloat16* __restrict__ d, const in
 // the additions, hence the last bits of dD, varies from run to run — as torch's index_add_ on CUDA).
 __global__ void flmr_bwd_dd_kernel(const __nv_bfloat16* __restrict__ q, const int32_t* __restrict__ arg,
                                    const float* __restrict__ g, int B, int nq, int n, int nd,
-                                   float* __restrict__ dd) {
+                                   int stride_b, float* __restrict__ dd) {
   const int64_t w = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (w >= static_cast<int64_t>(B) * n * nq) return;
@@ -278,7 +285,7 @@ __global__ void flmr_bwd_dd_kernel(const __nv_bfloat16* __restrict__ q, const in
   if (j < 0 || gp == 0.f) return;
   float f[4];
   bf16x4_to_float(*reinterpret_cast<const uint2*>(q + (static_cast<int64_t>(b) * nq + i) * 128 + lane * 4), f);
-  float* dst = dd + (static_cast<int64_t>(p) * nd + j) * 128 + lane * 4;
+  float* dst = dd + ((static_cast<int64_t>(b) * stride_b + p) * nd + j) * 128 + lane * 4;
 #pragma unroll
   for (int e = 0; e < 4; ++e) atomicAdd(dst + e, gp * f[e]);
 }

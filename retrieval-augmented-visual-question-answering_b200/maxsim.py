@@ -112,6 +112,49 @@ def _train_operands(Q: torch.Tensor, D_padded: torch.Tensor):
     return (Q.detach().to(torch.bfloat16).contiguous(), D_padded.detach().to(torch.bfloat16).contiguous())
 
 
+def maxsim_argmax_grouped(Q: torch.Tensor, D_padded: torch.Tensor, D_mask: torch.Tensor, docs_per_query: int,
+                          return_rowmax: bool = False):
+    """Block-diagonal ``maxsim_argmax``: query ``b`` meets only documents ``[b*r, (b+1)*r)``, ``r =
+    docs_per_query`` (``D_padded`` holds ``B*r`` documents).  Returns ``arg`` int32 ``[B, r, Nq]`` (and the
+    maxima, fp32, same shape): ``rowmax.sum(-1)`` is the aligned score matrix ``[B, r]``."""
+    Qb, Db = _train_operands(Q, D_padded)
+    B, nq, n, nd = Qb.size(0), Qb.size(1), Db.size(0), Db.size(1)
+    r = int(docs_per_query)
+    if r < 1 or n != B * r:
+        raise ValueError("expected %d x %d documents, got %d" % (B, r, n))
+    mask = D_mask.reshape(n, nd).to(device=Qb.device, dtype=torch.uint8).contiguous()
+    arg = torch.empty((B, r, nq), dtype=torch.int32, device=Qb.device)
+    rowmax = torch.empty((B, r, nq), dtype=torch.float32, device=Qb.device) if return_rowmax else None
+    with torch.cuda.device(Qb.device):
+        _cabi.check(_cabi.lib().flmr_maxsim_argmax_grouped(
+            C.c_void_p(Qb.data_ptr()), B, nq, C.c_void_p(Db.data_ptr()), C.c_void_p(mask.data_ptr()), r, nd,
+            C.c_void_p(arg.data_ptr()), C.c_void_p(rowmax.data_ptr() if return_rowmax else None),
+            int(Qb.device.index), C.c_void_p(torch.cuda.current_stream(Qb.device).cuda_stream)))
+    return (arg, rowmax) if return_rowmax else arg
+
+
+def maxsim_backward_grouped(Q: torch.Tensor, D_padded: torch.Tensor, arg: torch.Tensor, grad: torch.Tensor,
+                            need_dq: bool = True, need_dd: bool = True):
+    """Gradients of the block-diagonal scores ``[B, r]`` (see ``maxsim_argmax_grouped``): returns
+    (dQ fp32 ``[B, Nq, d]`` or None, dD fp32 ``[B*r, Nd, d]`` or None)."""
+    Qb, Db = _train_operands(Q, D_padded)
+    B, nq, n, nd = Qb.size(0), Qb.size(1), Db.size(0), Db.size(1)
+    r = arg.size(1) if arg.dim() == 3 else 0
+    if arg.shape != (B, r, nq) or arg.dtype != torch.int32 or grad.shape != (B, r) or n != B * r:
+        raise ValueError("arg must be int32 [B, r, Nq], grad [B, r] and D hold B*r documents")
+    g = grad.detach().to(torch.float32).contiguous()
+    a = arg.contiguous()
+    dq = torch.empty((B, nq, _cabi.DIM), dtype=torch.float32, device=Qb.device) if need_dq else None
+    dd = torch.empty((n, nd, _cabi.DIM), dtype=torch.float32, device=Qb.device) if need_dd else None
+    with torch.cuda.device(Qb.device):
+        _cabi.check(_cabi.lib().flmr_maxsim_backward_grouped(
+            C.c_void_p(Qb.data_ptr()), B, nq, C.c_void_p(Db.data_ptr()), r, nd, C.c_void_p(a.data_ptr()),
+            C.c_void_p(g.data_ptr()), C.c_void_p(dq.data_ptr() if need_dq else None),
+            C.c_void_p(dd.data_ptr() if need_dd else None), int(Qb.device.index),
+            C.c_void_p(torch.cuda.current_stream(Qb.device).cuda_stream)))
+    return dq, dd
+
+
 def maxsim_argmax(Q: torch.Tensor, D_padded: torch.Tensor, D_mask: torch.Tensor, return_rowmax: bool = False):
     """``arg[b, p, i]`` = index (into the padded document) of the unmasked token of document ``p`` with
     the largest inner product with query token ``Q[b, i]``; int32 ``[B, n, Nq]``, -1 for a fully masked

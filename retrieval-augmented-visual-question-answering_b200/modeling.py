@@ -27,7 +27,8 @@ from typing import Optional
 import torch
 
 from .corpus import FlatCorpus
-from .maxsim import maxsim_argmax, maxsim_backward, maxsim_scores
+from .maxsim import (maxsim_argmax, maxsim_argmax_grouped, maxsim_backward, maxsim_backward_grouped,
+                     maxsim_scores)
 
 
 # Below this many multiply-accumulates the whole forward is ONE launch of the arg-max kernel (scores =
@@ -39,16 +40,16 @@ _FUSED_SMALL_MAX_MACS = 1e11
 
 def _forward_scores(Q: torch.Tensor, D_padded: torch.Tensor, D_mask: torch.Tensor):
     """All-pairs scores ``[B, n]``; returns (scores, bool mask [n, Nd], saved arg-max or None)."""
-    if not (Q.is_cuda and D_padded.is_cuda):
-        raise RuntimeError("the scoring path is CUDA-only (no CPU fallback)")
     n, nd = D_padded.size(0), D_padded.size(1)
     mask = D_mask.reshape(n, nd).bool()
+    if float(Q.size(0)) * n * Q.size(1) * nd * Q.size(2) <= _FUSED_SMALL_MAX_MACS:
+        # no host round trip on the training path: a document without any unmasked token scores -inf here
+        # (its winners are -1 and it receives no gradient); the reference's padded path gives -9999 * Nq
+        arg, rowmax = maxsim_argmax(Q, D_padded, mask, return_rowmax=True)
+        return rowmax.sum(dim=-1), mask, arg
     if not bool(mask.any(dim=1).all()):
         raise ValueError("a document has no unmasked token: its MaxSim score is undefined "
                          "(-9999 * Nq on the reference's padded path)")
-    if float(Q.size(0)) * n * Q.size(1) * nd * Q.size(2) <= _FUSED_SMALL_MAX_MACS:
-        arg, rowmax = maxsim_argmax(Q, D_padded, mask, return_rowmax=True)
-        return rowmax.sum(dim=-1), mask, arg
     packed = D_padded.detach()[mask]
     corpus = FlatCorpus(packed.to(torch.bfloat16), mask.sum(dim=1).cpu(), device=Q.device, adopt=True)
     try:
@@ -81,57 +82,70 @@ class _AllPairsMaxSim(torch.autograd.Function):
                 dD.to(D_padded.dtype) if dD is not None else None, None)
 
 
-def _consecutive_runs(Q: torch.Tensor):
-    """Runs of identical consecutive queries: (one representative per run ``[U, Nq, d]``, run index of every
-    row ``[n]``).  Same result as ``torch.unique_consecutive(Q, dim=0, return_inverse=True)``, whose CUDA
-    implementation compares whole rows (Nq*d elements) serially in a single thread — ~80 ms per call for an
-    832-token query, measured — where two vectorised passes take microseconds."""
+def _equal_run_length(Q: torch.Tensor) -> int:
+    """``r`` if ``Q [n, Nq, d]`` consists of consecutive runs of exactly ``r`` identical queries each (what
+    ``repeat_interleave(r, dim=0)`` builds; adjacent runs differ), else 0.  Two vectorised passes and two scalar
+    read-backs — ``torch.unique_consecutive(Q, dim=0)`` compares whole rows serially in one CUDA thread (~80 ms
+    per call for an 832-token query, measured in round 1)."""
     n = Q.size(0)
-    if n == 1:
-        return Q, torch.zeros(1, dtype=torch.long, device=Q.device)
+    if n < 2:
+        return 0
+    Qd = Q.detach()
     new_run = torch.ones(n, dtype=torch.bool, device=Q.device)
-    new_run[1:] = (Q[1:] != Q[:-1]).flatten(1).any(dim=1)
-    inverse = torch.cumsum(new_run.long(), dim=0) - 1
-    return Q[new_run], inverse
+    new_run[1:] = (Qd[1:] != Qd[:-1]).flatten(1).any(dim=1)
+    starts = new_run.nonzero().flatten()
+    U = int(starts.numel())
+    r = n // U
+    if U * r != n or r < 2:
+        return 0
+    return r if bool((starts == torch.arange(U, device=Q.device) * r).all()) else 0
 
 
-class _AlignedMaxSim(torch.autograd.Function):
-    """scores[p] = MaxSim(Q[p], D[p]) for ``Q [n, Nq, d]`` aligned with ``D [n, Nd, d]``.
-
-    Callers build ``Q`` with ``repeat_interleave`` (colbert.py:71, rag_model_blip.py:433,
-    FLMR_executor.py:828): runs of identical queries are scored once against all documents (one scan
-    launch over the unique queries) and the aligned entries are gathered."""
+class _GroupedMaxSim(torch.autograd.Function):
+    """scores[b, t] = MaxSim(Q[b], D[b*r + t]) for ``Q [B, Nq, d]`` and ``D [B*r, Nd, d]``: query ``b`` against
+    ITS ``r`` documents only — the block diagonal of the all-pairs matrix, computed without the off-diagonal
+    pairs (one launch of the grouped arg-max kernel forward, saved winners, gather/scatter backward)."""
 
     @staticmethod
-    def forward(ctx, Q: torch.Tensor, D_padded: torch.Tensor, D_mask: torch.Tensor) -> torch.Tensor:
-        Qu, inverse = _consecutive_runs(Q.detach())
-        S, mask, arg = _forward_scores(Qu, D_padded, D_mask)
-        cols = torch.arange(D_padded.size(0), device=S.device)
-        ctx.has_arg = arg is not None
-        ctx.save_for_backward(Qu, D_padded, mask, inverse, *([arg] if ctx.has_arg else []))
-        ctx.q_dtype = Q.dtype
-        return S[inverse, cols]
+    def forward(ctx, Q: torch.Tensor, D_padded: torch.Tensor, D_mask: torch.Tensor, r: int) -> torch.Tensor:
+        n, nd = D_padded.size(0), D_padded.size(1)
+        mask = D_mask.reshape(n, nd).bool()
+        arg, rowmax = maxsim_argmax_grouped(Q, D_padded, mask, r, return_rowmax=True)
+        ctx.save_for_backward(Q, D_padded, arg)
+        return rowmax.sum(dim=-1)                                              # [B, r]
 
     @staticmethod
     def backward(ctx, grad: torch.Tensor):
-        Qu, D_padded, mask, inverse = ctx.saved_tensors[:4]
+        Q, D_padded, arg = ctx.saved_tensors
         need_dq, need_dd = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         if not (need_dq or need_dd):
-            return None, None, None
-        n = D_padded.size(0)
-        cols = torch.arange(n, device=grad.device)
-        arg = ctx.saved_tensors[4] if ctx.has_arg else maxsim_argmax(Qu, D_padded, mask)   # [U, n, Nq]
-        dQ = dD = None
-        if need_dd:
-            G = torch.zeros((Qu.size(0), n), dtype=torch.float32, device=grad.device)
-            G[inverse, cols] = grad.float()
-            dD = maxsim_backward(Qu, D_padded, arg, G, need_dq=False, need_dd=True)[1].to(D_padded.dtype)
-        if need_dq:                                                            # row p: grad[p] * D[p, arg[p]]
-            idx = arg[inverse, cols].long().clamp_min(0)                       # [n, Nq]
-            Dsel = D_padded.detach().to(torch.bfloat16).float().gather(
-                1, idx.unsqueeze(-1).expand(-1, -1, D_padded.size(2)))
-            dQ = (grad.float()[:, None, None] * Dsel).to(ctx.q_dtype)
-        return dQ, dD, None
+            return None, None, None, None
+        dQ, dD = maxsim_backward_grouped(Q, D_padded, arg, grad, need_dq=need_dq, need_dd=need_dd)
+        return (dQ.to(Q.dtype) if dQ is not None else None,
+                dD.to(D_padded.dtype) if dD is not None else None, None, None)
+
+
+def grouped_maxsim(Q: torch.Tensor, D_padded: torch.Tensor, D_mask: torch.Tensor, docs_per_query: int
+                   ) -> torch.Tensor:
+    """``[B, r]`` scores of every query against its own ``r = docs_per_query`` documents (differentiable):
+    ``ColBERT.score(Q.repeat_interleave(r, 0), D, D_mask).view(B, r)`` (colbert.py:71-73) without the repeat."""
+    return _GroupedMaxSim.apply(Q, D_padded, D_mask, int(docs_per_query))
+
+
+def _aligned_maxsim(Q: torch.Tensor, D_padded: torch.Tensor, D_mask: torch.Tensor) -> torch.Tensor:
+    """scores[p] = MaxSim(Q[p], D[p]) for ``Q [n, Nq, d]`` aligned with ``D [n, Nd, d]``.
+
+    Callers build ``Q`` with ``repeat_interleave`` (colbert.py:71, rag_model_blip.py:433,
+    FLMR_executor.py:828).  Runs of identical consecutive queries are detected on the device; equal-length
+    runs (the ``repeat_interleave`` form: U queries x r documents each) become ONE grouped launch over the U
+    unique queries, anything else a grouped launch with one document per query.  Either way only the n
+    aligned pairs are scored — O(n), where scoring all U x n pairs and gathering would be O(U n)."""
+    n = D_padded.size(0)
+    r = _equal_run_length(Q)
+    if r:
+        # differentiable pick of one representative per run; its gradient is the sum over the run's rows
+        return _GroupedMaxSim.apply(Q[::r], D_padded, D_mask, r).reshape(n)
+    return _GroupedMaxSim.apply(Q, D_padded, D_mask, 1).reshape(n)
 
 
 def all_pairs_maxsim(Q: torch.Tensor, D_padded: torch.Tensor, D_mask: torch.Tensor) -> torch.Tensor:
@@ -148,13 +162,14 @@ def colbert_score(Q: torch.Tensor, D_padded: torch.Tensor, D_mask: torch.Tensor,
     semantics of the padded path."""
     assert Q.dim() == 3 and D_padded.dim() == 3, (Q.size(), D_padded.size())
     assert Q.size(0) in [1, D_padded.size(0)]
-    if not use_gpu and not Q.is_cuda:
-        raise RuntimeError("this colbert_score is the CUDA path; there is no CPU fallback")
-    dev = Q.device if Q.is_cuda else torch.device("cuda", torch.cuda.current_device())
-    Q, D_padded, D_mask = Q.to(dev), D_padded.to(dev), D_mask.to(dev)
+    del config, use_gpu          # the reference moves the operands to the GPU when use_gpu is set; here ALWAYS
+    if torch.cuda.is_available():   # (without CUDA the kernels below raise: there is no CPU fallback)
+        dev = Q.device if Q.is_cuda else (D_padded.device if D_padded.is_cuda
+                                          else torch.device("cuda", torch.cuda.current_device()))
+        Q, D_padded, D_mask = Q.to(dev), D_padded.to(dev), D_mask.to(dev)
     if Q.size(0) == 1:
         return all_pairs_maxsim(Q, D_padded, D_mask)[0]
-    return _AlignedMaxSim.apply(Q, D_padded, D_mask)
+    return _aligned_maxsim(Q, D_padded, D_mask)
 
 
 class _GatherCat(torch.autograd.Function):

@@ -12,7 +12,7 @@ from __future__ import annotations
 import ctypes as C
 import json
 import os
-from typing import Tuple
+from typing import Optional, Tuple
 
 import numpy as np
 import torch
@@ -48,8 +48,19 @@ def decode_chunk(codes: torch.Tensor, residuals: torch.Tensor, centroids: torch.
             C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
 
 
-def plaid_to_flat(path: str, device=None) -> Tuple[torch.Tensor, np.ndarray]:
-    """Decode a whole PLAID index: returns (tokens bf16 ``[n_tokens, 128]`` on the GPU, doclens int32)."""
+def read_plaid_doclens(path: str, num_chunks: int):
+    """Per-chunk passage lengths (``doclens.<c>.json``, index_saver.py:83-85)."""
+    out = []
+    for c in range(num_chunks):
+        with open(os.path.join(path, "doclens.%d.json" % c)) as f:
+            out.append(np.asarray(json.load(f), dtype=np.int64))
+    return out
+
+
+def plaid_to_flat(path: str, device=None, passage_range: Optional[Tuple[int, int]] = None
+                  ) -> Tuple[torch.Tensor, np.ndarray]:
+    """Decode a PLAID index — all of it, or the passages ``[p0, p1)`` only (one GPU's shard: only the chunks
+    that overlap are read) — into (tokens bf16 ``[n_tokens, 128]`` on the GPU, doclens int32)."""
     if not torch.cuda.is_available():
         raise RuntimeError("PLAID decode runs on the GPU; there is no CPU fallback")
     device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
@@ -61,19 +72,26 @@ def plaid_to_flat(path: str, device=None) -> Tuple[torch.Tensor, np.ndarray]:
     centroids = torch.load(os.path.join(path, "centroids.pt"), map_location="cpu").float().to(device).contiguous()
     _cutoffs, weights = torch.load(os.path.join(path, "buckets.pt"), map_location="cpu")
     weights = weights.float().to(device).contiguous()
-    doclens, sizes = [], []
-    for c in range(meta["num_chunks"]):
-        with open(os.path.join(path, "doclens.%d.json" % c)) as f:
-            dl = json.load(f)
-        doclens.extend(dl)
-        sizes.append(int(sum(dl)))
-    tokens = torch.empty((sum(sizes), _cabi.DIM), dtype=torch.bfloat16, device=device)
+    chunk_doclens = read_plaid_doclens(path, meta["num_chunks"])
+    n_total = int(sum(len(d) for d in chunk_doclens))
+    p0, p1 = (0, n_total) if passage_range is None else passage_range
+    if not 0 <= p0 <= p1 <= n_total:
+        raise ValueError("passage_range %s outside [0, %d]" % (passage_range, n_total))
+    pieces, c0 = [], 0                       # (chunk, first token row, one-past-last row, doclens slice)
+    for c, dl in enumerate(chunk_doclens):
+        a, b = max(p0, c0) - c0, min(p1, c0 + len(dl)) - c0
+        if a < b:
+            off = np.concatenate([[0], np.cumsum(dl)])
+            pieces.append((c, int(off[a]), int(off[b]), dl[a:b], int(off[-1])))
+        c0 += len(dl)
+    tokens = torch.empty((sum(p[2] - p[1] for p in pieces), _cabi.DIM), dtype=torch.bfloat16, device=device)
     row = 0
-    for c, n in enumerate(sizes):
+    for c, r0, r1, _, n_chunk in pieces:
         codes = torch.load(os.path.join(path, "%d.codes.pt" % c), map_location="cpu")
         residuals = torch.load(os.path.join(path, "%d.residuals.pt" % c), map_location="cpu")
-        if codes.numel() != n:
-            raise ValueError("chunk %d holds %d codes but its doclens sum to %d" % (c, codes.numel(), n))
-        decode_chunk(codes, residuals, centroids, weights, meta["nbits"], tokens[row:row + n])
-        row += n
-    return tokens, np.asarray(doclens, dtype=np.int32)
+        if codes.numel() != n_chunk:
+            raise ValueError("chunk %d holds %d codes but its doclens sum to %d" % (c, codes.numel(), n_chunk))
+        decode_chunk(codes[r0:r1], residuals[r0:r1], centroids, weights, meta["nbits"], tokens[row:row + r1 - r0])
+        row += r1 - r0
+    doclens = np.concatenate([p[3] for p in pieces]) if pieces else np.empty(0, dtype=np.int64)
+    return tokens, doclens.astype(np.int32)

@@ -1,56 +1,108 @@
 """``Searcher`` façade with the call surface of the reference's ``colbert.Searcher``
-(third_party/ColBERT/colbert/searcher.py:22-132) so ``src/executors/FLMR_executor.py:785-792`` and
-``src/models/rag/rag_model_blip.py:397`` can call it unchanged:
+(third_party/ColBERT/colbert/searcher.py:22-132) so ``src/executors/FLMR_executor.py:774-792`` and
+``src/models/rag/rag_model_blip.py:297-301, 397`` run unchanged:
 
-    Searcher(index=..., checkpoint=None, collection=None, config=None)
+    with Run().context(RunConfig(nranks=1, rank=..., root=..., experiment=...)):
+        searcher = Searcher(index="temp_index.nbits=8", config=ColBERTConfig(total_visible_gpus=...))
     ._search_all_Q(queries, Q, k, filter_fn=None, progress=True, remove_zero_tensors=False) -> Ranking
     .dense_search(Q[1,Nq,d], k, filter_fn=None, remove_zero_tensors=False) -> (pids, ranks, scores)
     .search(text, k) / .search_all(queries, k)        (need an ``encode_fn``: encoders stay PyTorch)
     Ranking.todict() -> {qid: [(pid, rank, score), ...]}   (colbert/data/ranking.py:48)
 
+The index is addressed exactly as the reference does (``<Run().root>/<experiment>/indexes/<index>``,
+infra.resolve_index_path) and whatever lives there is opened: a flat index written by this package's
+``Indexer`` (index_io.py), or a PLAID directory written by the reference's own ``Indexer`` — decoded on the
+GPU into the flat bf16 store (plaid.py).
+
 What differs, by design: scoring is exhaustive and exact (no PLAID candidate
 generation / centroid pruning), all queries of a call go through one batched fused scan instead of
 a Python loop of per-query ``rank`` calls, and results always hold exactly ``min(k, n_passages)``
-hits.
+hits.  ``shard_across_ranks=True`` (an extension; needs an initialised ``torch.distributed`` group) keeps
+only this rank's passage shard resident and merges the per-shard top-k with one all-gather, where the
+reference repeats the whole search on every rank (FLMR_executor.py:778-781).
 """
 from __future__ import annotations
 
 import json
 import os
-from typing import Callable, Dict, Iterable, List, Optional, Tuple, Union
+from typing import Callable, Dict, List, Optional, Tuple, Union
 
 import torch
 
 from . import _cabi
 from .corpus import FlatCorpus
-from .index_io import load_flat_index
+from .index_io import FORMAT as FLAT_FORMAT
+from .infra import ColBERTConfig, active_run_config, resolve_index_path
 from .maxsim import maxsim_scores, maxsim_topk, topk_select
 
 
 class Ranking:
-    """Minimal equivalent of colbert.data.Ranking (colbert/data/ranking.py:25-94): ``data`` maps
-    qid -> [(pid, rank (1-based), score), ...]."""
+    """colbert.data.Ranking (colbert/data/ranking.py:25-94): ``data`` maps qid -> [(pid, rank (1-based),
+    score), ...]; ``flat_ranking`` / ``tolist`` is the same as (qid, pid, rank, score) rows; ``save`` writes
+    the reference's TSV plus a ``.meta`` JSON with the provenance."""
 
-    def __init__(self, data: Dict, provenance: Optional[dict] = None):
-        self.data = data
-        self.provenance_ = provenance or {}
+    def __init__(self, path: Optional[str] = None, data=None, metrics=None, provenance=None):
+        del metrics
+        self._provenance = provenance if provenance is not None else (path or {})
+        if data is None:
+            if path is None:
+                raise ValueError("Ranking needs data= or path=")
+            data = self._load_file(path)
+        if isinstance(data, dict):
+            self.flat_ranking = [(qid, *rest) for qid, sub in data.items() for rest in sub]
+            self.data = data
+        else:                                       # flat rows: group by qid, order preserved
+            self.flat_ranking = [tuple(r) for r in data]
+            grouped: Dict = {}
+            for qid, *rest in self.flat_ranking:
+                grouped.setdefault(qid, []).append(tuple(rest))
+            self.data = grouped
+
+    @staticmethod
+    def _load_file(path: str):
+        def num(v):
+            return float(v) if "." in v else int(v)
+        with open(path) as f:
+            return [list(map(num, line.strip().split("\t"))) for line in f if line.strip()]
 
     def provenance(self):
-        return self.provenance_
+        return self._provenance
+
+    def toDict(self):
+        return {"provenance": self.provenance()}
 
     def todict(self):
         return dict(self.data)
 
     def tolist(self):
-        return [(qid, pid, rank, score) for qid, hits in self.data.items() for pid, rank, score in hits]
+        return list(self.flat_ranking)
 
-    def save(self, path: str) -> str:
-        with open(path, "w") as f:
-            for qid, pid, rank, score in self.tolist():
-                f.write("\t".join(map(str, (qid, pid, rank, score))) + "\n")
-        with open(path + ".meta", "w") as f:
-            json.dump(self.provenance_, f)
-        return path
+    def items(self):
+        return self.data.items()
+
+    def save(self, new_path: str) -> str:
+        """ranking.py:64-82.  The reference resolves ``new_path`` under ``Run().path_`` (a per-script
+        timestamped directory); here a relative path is taken as given."""
+        assert "tsv" in new_path.strip("/").split("/")[-1].split("."), "TODO: Support .json[l] too."
+        os.makedirs(os.path.dirname(os.path.abspath(new_path)), exist_ok=True)
+        with open(new_path, "w") as f:
+            for items in self.flat_ranking:
+                f.write("\t".join(str(int(x) if type(x) is bool else x) for x in items) + "\n")
+        prov = self.provenance()
+        with open(new_path + ".meta", "w") as f:
+            json.dump({"metadata": {}, "provenance": prov.toDict() if hasattr(prov, "toDict") else prov},
+                      f, indent=4, default=str)
+        return new_path
+
+    @classmethod
+    def cast(cls, obj):
+        if type(obj) is str:
+            return cls(path=obj)
+        if isinstance(obj, (dict, list)):
+            return cls(data=obj)
+        if type(obj) is cls:
+            return obj
+        assert False, "obj has type %s which is not compatible with cast()" % type(obj)
 
 
 def _query_keys(queries, n: int) -> List:
@@ -65,37 +117,87 @@ def _query_keys(queries, n: int) -> List:
     return keys
 
 
+def detect_index_kind(path: str) -> str:
+    """'flat' (index_io.py) or 'plaid' (the reference's format) for the directory the
+    reference's ``ColBERTConfig.load_from_index`` (base_config.py:71-87) would read its config from."""
+    meta_path = os.path.join(path, "metadata.json")
+    if os.path.exists(meta_path):
+        with open(meta_path) as f:
+            meta = json.load(f)
+        if meta.get("format") == FLAT_FORMAT:
+            return "flat"
+        if "nbits" in meta.get("config", {}) and os.path.exists(os.path.join(path, "centroids.pt")):
+            return "plaid"
+        raise ValueError("%s holds a metadata.json that is neither a %s index nor a PLAID index "
+                         "(config.nbits + centroids.pt)" % (path, FLAT_FORMAT))
+    if os.path.exists(os.path.join(path, "plan.json")):
+        raise ValueError("%s holds only plan.json: the PLAID index build did not finish "
+                         "(collection_indexer.py:428-444 writes metadata.json last)" % path)
+    raise FileNotFoundError("no index at %s (no metadata.json)" % path)
+
+
 class Searcher:
     def __init__(self, index: Union[str, FlatCorpus], checkpoint=None, collection=None, config=None,
                  disable_gpu: bool = True, device: Optional[Union[int, torch.device]] = None,
                  encode_fn: Optional[Callable] = None, index_root: Optional[str] = None,
-                 query_batch: int = 64):
+                 query_batch: int = 64, shard_across_ranks: bool = False, group=None):
         # `disable_gpu` is part of the reference signature (default True) but dead there: colbert/searcher.py:23
         # never reads it, the device is chosen by config.total_visible_gpus (:40-43), which FLMR_executor.py:778-781
         # zeroes under DDP to force CPU search.  Here the search always runs on the GPU (no CPU path exists);
         # FlatCorpus raises when CUDA is absent.
         del disable_gpu
-        self.config = config
         self.checkpoint = checkpoint
         self.collection = collection
         self.encode_fn = encode_fn
         self.query_batch = int(query_batch)
+        self._sharded = None
+        self.index_config = None
+        run_cfg = active_run_config(config)
         if isinstance(index, FlatCorpus):
             self.corpus = index
             self.index = None
+            self.index_kind = "resident"
         else:
-            root = index_root or (getattr(config, "index_root_", None) if config is not None else None)
-            path = index if os.path.isabs(index) or root is None else os.path.join(root, index)
-            tokens, doclens, meta = load_flat_index(path)
-            self.index = path
-            self.corpus = FlatCorpus(tokens, doclens, device=device)
+            # searcher.py:26-30: index path = <index_root_ of from_existing(config, Run().config)>/<index>
+            self.index = resolve_index_path(index, config, index_root)
+            self.index_kind = detect_index_kind(self.index)
+            self.index_config = ColBERTConfig.load_from_index(self.index) if self.index_kind == "plaid" else None
+            rank, world = 0, 1
+            if shard_across_ranks:
+                import torch.distributed as dist
+                if not (dist.is_available() and dist.is_initialized()):
+                    raise RuntimeError("shard_across_ranks needs an initialised torch.distributed process group")
+                rank, world = dist.get_rank(group), dist.get_world_size(group)
+            if self.index_kind == "flat":
+                self.corpus = FlatCorpus.from_index(self.index, device=device, rank=rank, world_size=world)
+            else:
+                self.corpus = FlatCorpus.from_plaid(self.index, device=device, rank=rank, world_size=world)
+        # searcher.py:35: checkpoint config < index config < (config + Run().config); kept for callers that
+        # read searcher.config — none of its PLAID knobs influence the exhaustive scan.
+        cfg_type = type(config) if (config is not None and hasattr(type(config), "from_existing")) else ColBERTConfig
+        try:
+            self.config = cfg_type.from_existing(self.index_config if cfg_type is ColBERTConfig else None,
+                                                 config, run_cfg)
+        except Exception:          # foreign config type with a different constructor: keep what was given
+            self.config = config
+        if shard_across_ranks:
+            from .maxsim import topk_merge
+            from .sharded import ShardedSearcher
+            self._sharded = ShardedSearcher(None, lambda s, p, k: topk_merge(s, p, k), group)
+        if self.corpus is not None:
+            self.device = self.corpus.device
+        else:
+            self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self._relu = False
 
     # -- reference-compatible surface ------------------------------------------------------------
     def configure(self, **kw):
         """colbert.Searcher.configure (searcher.py:49-50).  PLAID knobs (ncells,
-        centroid_score_threshold, ndocs) are accepted and ignored: the scan is exhaustive."""
+        centroid_score_threshold, ndocs) are recorded on ``config`` and otherwise ignored: the scan is
+        exhaustive."""
         self._relu = bool(kw.pop("relu", self._relu))
+        if kw and self.config is not None and hasattr(self.config, "configure"):
+            self.config.configure(**kw)
         return self
 
     def encode(self, text, full_length_search=False):
@@ -112,37 +214,74 @@ class Searcher:
         texts = list(queries.values()) if hasattr(queries, "values") else list(queries)
         return self._search_all_Q(queries, self.encode(texts), k, filter_fn=filter_fn)
 
-    def _search_tensors(self, Q: torch.Tensor, k: int, filter_fn=None) -> Tuple[torch.Tensor, torch.Tensor]:
-        """(scores [B,k'], pids [B,k']) on the GPU, k' = min(k, n_passages)."""
-        n = self.corpus.n_passages
-        kk = min(int(k), n)
-        if filter_fn is None and kk <= _cabi.MAX_K:
+    @staticmethod
+    def _drop_zero_rows(Q: torch.Tensor) -> torch.Tensor:
+        """``remove_zero_tensors`` (searcher.py:120-126) for a batch: all-zero query rows are dropped and the
+        remaining rows of every query packed to the front (order kept), padded with zero rows to the longest
+        query of the batch.  A zero row adds ``max_j 0 = 0`` to every passage, so scores are unchanged; the
+        scan just has fewer rows to go through (WIT pre-training queries: 32 live rows out of 32 + text)."""
+        live = Q.abs().sum(dim=-1) > 0                                   # [B, Nq]
+        n_live = int(live.sum(dim=1).max().item()) if Q.numel() else 0
+        if n_live == Q.size(1):
+            return Q
+        order = torch.argsort((~live).to(torch.int8), dim=1, stable=True)[:, :max(n_live, 1)]
+        return torch.gather(Q, 1, order.unsqueeze(-1).expand(-1, -1, Q.size(2)))
+
+    def _local_topk(self, Q: torch.Tensor, kk: int, keep: Optional[torch.Tensor]) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Top-``kk`` of this shard: (scores [B, kk'], global pids [B, kk']), kk' = min(kk, candidates)."""
+        corpus = self.corpus
+        if corpus is None:                               # this rank's shard is empty (more ranks than passages)
+            return (torch.empty((Q.size(0), 0), dtype=torch.float32, device=self.device),
+                    torch.empty((Q.size(0), 0), dtype=torch.int64, device=self.device))
+        if keep is None and kk <= _cabi.MAX_K:
+            kq = min(kk, corpus.n_passages)
             outs, outp = [], []
             for b0 in range(0, Q.size(0), self.query_batch):
-                s, p = maxsim_topk(self.corpus, Q[b0:b0 + self.query_batch], kk, relu=self._relu)
+                s, p = maxsim_topk(corpus, Q[b0:b0 + self.query_batch], kq, relu=self._relu)
                 outs.append(s)
                 outp.append(p)
             return torch.cat(outs), torch.cat(outp)
         # filtered or very large k: all scores from the fused scan, selection as plain plumbing
         outs, outp = [], []
-        keep = None
-        if filter_fn is not None:
-            all_pids = torch.arange(n, device=self.corpus.device) + self.corpus.pid_base
-            keep = torch.as_tensor(filter_fn(all_pids), device=self.corpus.device).long() - self.corpus.pid_base
+        n_cand = corpus.n_passages if keep is None else int(keep.numel())
+        kq = min(kk, n_cand)
+        if kq == 0:
+            return (torch.empty((Q.size(0), 0), dtype=torch.float32, device=corpus.device),
+                    torch.empty((Q.size(0), 0), dtype=torch.int64, device=corpus.device))
         for b0 in range(0, Q.size(0), self.query_batch):
-            s = maxsim_scores(self.corpus, Q[b0:b0 + self.query_batch], relu=self._relu)
+            s = maxsim_scores(corpus, Q[b0:b0 + self.query_batch], relu=self._relu)
             if keep is not None:
                 s = s[:, keep]
-            kq = min(kk, s.size(1))
             if kq <= _cabi.SELECT_MAX_K:
                 vals, idx = topk_select(s, kq)                       # radix-select kernel
             else:
                 vals, idx = torch.sort(s, dim=1, descending=True, stable=True)
                 vals, idx = vals[:, :kq], idx[:, :kq]
-            pids = (keep[idx] if keep is not None else idx) + self.corpus.pid_base
             outs.append(vals)
-            outp.append(pids)
+            outp.append((keep[idx] if keep is not None else idx) + corpus.pid_base)
         return torch.cat(outs), torch.cat(outp)
+
+    def _search_tensors(self, Q: torch.Tensor, k: int, filter_fn=None,
+                        remove_zero_tensors: bool = False) -> Tuple[torch.Tensor, torch.Tensor]:
+        """(scores [B,k'], pids [B,k']) on the GPU, k' = min(k, passages that pass ``filter_fn``)."""
+        if Q.dim() == 2:
+            Q = Q.unsqueeze(0)
+        if remove_zero_tensors:
+            Q = self._drop_zero_rows(Q)
+        corpus = self.corpus
+        keep = None
+        if filter_fn is not None and corpus is not None:
+            all_pids = torch.arange(corpus.n_passages, device=corpus.device) + corpus.pid_base
+            keep = torch.as_tensor(filter_fn(all_pids), device=corpus.device).long() - corpus.pid_base
+        s, p = self._local_topk(Q, int(k), keep)
+        if self._sharded is not None:
+            k_merge = int(k)
+            if k_merge > _cabi.MAX_K:
+                raise ValueError("sharded search merges at most k=%d results per query" % _cabi.MAX_K)
+            s, p = self._sharded.exchange(s.to(self.device), p.to(self.device), k_merge)
+            n_valid = int((p[0] >= 0).sum()) if p.numel() else 0    # same for every query: min(k, candidates)
+            s, p = s[:, :n_valid], p[:, :n_valid]
+        return s, p
 
     def retrieve_and_rescore(self, Q: torch.Tensor, n_docs: int, generator: Optional[torch.Generator] = None):
         """The retrieval block of ``RagModelForBlip.main_retrieve`` (src/models/rag/rag_model_blip.py:388-443)
@@ -154,9 +293,12 @@ class Searcher:
         (no host dictionary, no H2D copy).  Returns a dict with ``doc_scores [B, n_docs]`` (differentiable
         w.r.t. ``Q``), ``retrieved_doc_ids`` (int64 numpy ``[B, n_docs]``, as :441), ``search_scores``, and the
         gathered ``item_embeddings [B, n_docs, Nd, d]`` / ``item_mask [B, n_docs, Nd, 1]``."""
-        from .modeling import all_pairs_maxsim, colbert_score
+        from .modeling import grouped_maxsim
         if Q.dim() != 3:
             raise ValueError("Q must be [B, Nq, d]")
+        if self._sharded is not None:
+            raise RuntimeError("retrieve_and_rescore gathers embeddings from the local shard only; "
+                               "use an unsharded Searcher for the RAG block")
         n_retrieve = max(5, int(n_docs))
         Qd = Q.to(self.corpus.device)
         s, p = self._search_tensors(Qd.detach(), n_retrieve)
@@ -166,29 +308,17 @@ class Searcher:
             pick = torch.rand(s.shape, generator=generator, device="cpu").argsort(dim=1)[:, :n_docs].to(s.device)
             s, p = s.gather(1, pick), p.gather(1, pick)
         D, mask = self.corpus.gather_padded(p)                               # [B, n_docs, Nd, d]
-        B = Qd.size(0)
-        if B <= 16:
-            # one launch: every question against every retrieved passage, keep the block diagonal (the extra
-            # pairs cost less than B separate launches; their upstream gradient is zero and is skipped)
-            S = all_pairs_maxsim(Qd, D.flatten(0, 1), mask.flatten(0, 1))    # [B, B * n_docs]
-            cols = torch.arange(B, device=S.device)[:, None] * n_docs + torch.arange(n_docs, device=S.device)
-            doc_scores = S.gather(1, cols)
-        else:
-            doc_scores = torch.stack([
-                colbert_score(Qd[b:b + 1].repeat_interleave(n_docs, dim=0), D[b], mask[b]) for b in range(B)])
+        # one block-diagonal launch: question b against ITS n_docs passages only
+        doc_scores = grouped_maxsim(Qd, D.flatten(0, 1), mask.flatten(0, 1), n_docs)
         return {"doc_scores": doc_scores, "retrieved_doc_ids": p.cpu().numpy(), "search_scores": s,
                 "item_embeddings": D, "item_mask": mask}
 
     def dense_search(self, Q: torch.Tensor, k: int = 10, filter_fn=None, remove_zero_tensors: bool = False):
-        """searcher.py:91-132 -> ``(pids[:k], [1..k], scores[:k])`` for ONE query ``Q [1, Nq, d]``.
-
-        ``remove_zero_tensors`` (searcher.py:120-126) is accepted for compatibility: all-zero query
-        rows contribute exactly 0 to every passage here, so dropping them cannot change the result.
-        """
+        """searcher.py:91-132 -> ``(pids[:k], [1..k], scores[:k])`` for ONE query ``Q [1, Nq, d]``."""
         if Q.dim() == 2:
             Q = Q.unsqueeze(0)
         assert Q.size(0) == 1, "dense_search takes a single query (use _search_all_Q for batches)"
-        s, p = self._search_tensors(Q, k, filter_fn)
+        s, p = self._search_tensors(Q, k, filter_fn, remove_zero_tensors)
         pids, scores = p[0].tolist(), s[0].tolist()
         return pids, list(range(1, len(pids) + 1)), scores
 
@@ -196,11 +326,16 @@ class Searcher:
                       remove_zero_tensors: bool = False) -> Ranking:
         """searcher.py:73-89, batched: one fused scan per ``query_batch`` queries instead of a Python
         loop of per-query ``dense_search`` calls."""
+        del progress
         keys = _query_keys(queries, Q.size(0))
-        s, p = self._search_tensors(Q, k, filter_fn)
+        s, p = self._search_tensors(Q, k, filter_fn, remove_zero_tensors)
         s, p = s.cpu().tolist(), p.cpu().tolist()
         data = {qid: [(pid, rank + 1, score) for rank, (pid, score) in enumerate(zip(pp, ss))]
                 for qid, pp, ss in zip(keys, p, s)}
-        prov = {"source": "ravqa_b200.Searcher::search_all", "k": k,
-                "n_passages": self.corpus.n_passages, "exhaustive": True}
+        prov = {"source": "Searcher::search_all", "k": k,
+                "queries": queries.provenance() if hasattr(queries, "provenance") else None,
+                "config": self.config.export() if hasattr(self.config, "export") else None,
+                "backend": "ravqa_b200 exhaustive fused scan", "index": self.index,
+                "index_kind": self.index_kind, "exhaustive": True,
+                "n_passages": self.corpus.n_passages if self.corpus is not None else 0}
         return Ranking(data=data, provenance=prov)

@@ -49,14 +49,27 @@ class ShardedSearcher:
 
     def search(self, Q: torch.Tensor, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
         s, p = self.local_topk(Q, k)
+        return self.exchange(s, p, k)
+
+    def exchange(self, s: torch.Tensor, p: torch.Tensor, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
+        """The one exchange step: all-gather of every rank's ``[B, k_local]`` list, then the merge.  Scores
+        travel as their bit patterns next to the pids in ONE pre-shaped int64 buffer (one collective, no
+        per-rank tensor list); a shard with fewer than ``k`` passages pads its list with (-inf, -1) entries,
+        which the merge ignores."""
         world = dist.get_world_size(self.group) if dist.is_initialized() else 1
         if world == 1:
             return self.merge(s.unsqueeze(0), p.unsqueeze(0), k)
-        # one exchange step: score bits and pids travel together as int64 pairs [B, k, 2]
-        payload = torch.stack([s.contiguous().view(torch.int32).to(torch.int64), p.contiguous()], dim=-1)
-        gathered = [torch.empty_like(payload) for _ in range(world)]
-        dist.all_gather(gathered, payload, group=self.group)
-        g = torch.stack(gathered)
-        gs = g[..., 0].to(torch.int32).view(torch.float32)
-        gp = g[..., 1]
-        return self.merge(gs.contiguous(), gp.contiguous(), k)
+        B, kl = s.shape
+        if kl < k:                                  # short shard (k > its passages, or an empty filter)
+            s = torch.cat([s, s.new_full((B, k - kl), float("-inf"))], dim=1)
+            p = torch.cat([p, p.new_full((B, k - kl), -1)], dim=1)
+        payload = torch.empty((2, B, k), dtype=torch.int64, device=s.device)
+        payload[0] = s.contiguous().view(torch.int32)
+        payload[1] = p
+        gathered = torch.empty((world, 2, B, k), dtype=torch.int64, device=s.device)
+        if dist.get_backend(self.group) == "nccl":
+            dist.all_gather_into_tensor(gathered, payload, group=self.group)
+        else:                                        # gloo (CPU tests) has no flat all-gather
+            dist.all_gather(list(gathered.unbind(0)), payload, group=self.group)
+        gs = gathered[:, 0].to(torch.int32).view(torch.float32)
+        return self.merge(gs, gathered[:, 1], k)

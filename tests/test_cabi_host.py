@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(L, n), "missing export " + n
     assert set(names) == set(_cabi.SYMBOLS)
-    assert L.flmr_abi_version() == 1
+    assert L.flmr_abi_version() == 2
 
 
 def header_prototypes():
