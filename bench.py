@@ -51,7 +51,30 @@ def parse_args():
     ap.add_argument("--plaid-passages", type=int, default=50_000,
                     help="passages in the sample PLAID index of the PLAID CPU-search baseline leg")
     ap.add_argument("--plaid-ndocs", type=int, default=1024, help="ndocs of the PLAID leg (reference default 1024)")
+    ap.add_argument("--no-c2", action="store_true", help="skip the C2-shaped (112k ragged passages, Nq=832, k=100) record")
+    ap.add_argument("--c2-passages", type=int, default=112_000)
     return ap.parse_args()
+
+
+def workload_config(args, world):
+    """The `config` object of the JSON line — built by ONE function for both arms (`--impl ours` and
+    `--impl reference`), so the driver compares like with like; arm-specific detail lives in other keys."""
+    return {"workload": "FLMR MaxSim top-%d: %d passages x Nd=%d, Nq=%d, d=128, batch %d queries/step"
+                        % (args.k, args.passages, args.nd, args.nq, args.batch),
+            "n_passages": args.passages, "nd": args.nd, "nq": args.nq, "dim": 128, "k": args.k,
+            "batch": args.batch, "parallelism": "passage-shard x%d + allgather(top-k)" % world,
+            "l2": "inputs larger than L2 (%.1f GB of passage tokens per GPU per pass)"
+                  % (args.passages * args.nd * 256 / world / 1e9)}
+
+
+def kernel_source_sha():
+    """Hash of the scan kernel's sources: the committed ncu traffic figure is only reported while it matches."""
+    import hashlib
+    h = hashlib.sha256()
+    for fn in ("flmr_scan_kernel.cuh", "flmr_device.cuh"):
+        with open(os.path.join(ROOT, "retrieval-augmented-visual-question-answering_b200", "csrc", fn), "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()[:16]
 
 
 def load_peaks():
@@ -68,9 +91,46 @@ def load_peaks():
 # reference CPU leg (oracle/_ref when the reference's segmented_maxsim.cpp was compiled, else the
 # oracle port).  TEST/BASELINE INFRASTRUCTURE: never on the product path.
 # --------------------------------------------------------------------------------------------------
+def _reference_packed_scorer():
+    """The reference's OWN ``colbert_score_packed`` (colbert.py:289-311) imported from /root/reference behind the
+    import shims of SURVEY.md Appendix A — build container only; the GPU box has no reference checkout."""
+    ref = "/root/reference/third_party/ColBERT"
+    if not os.path.isdir(ref):
+        return None
+    try:
+        import dataclasses
+        import torch
+        import transformers
+        sys.modules.setdefault("ujson", json)
+        _orig = dataclasses.dataclass
+
+        def _patched(cls=None, /, **kw):
+            def wrap(c):
+                c = _orig(c, **kw)
+                if c.__name__ == "DefaultVal":
+                    c.__hash__ = object.__hash__
+                return c
+            return wrap if cls is None else wrap(cls)
+        dataclasses.dataclass = _patched
+        if not hasattr(transformers, "AdamW"):
+            transformers.AdamW = torch.optim.AdamW
+        sys.path.insert(0, ref)
+        os.environ.setdefault("TORCH_EXTENSIONS_DIR", "/tmp/flmr_ref_torch_ext")
+        from colbert.infra.config import ColBERTConfig
+        from colbert.modeling.colbert import ColBERT, colbert_score_packed
+        ColBERT.try_load_torch_extensions(False)
+        cfg = ColBERTConfig(total_visible_gpus=0)
+        return lambda Q, D, doclens: colbert_score_packed(Q.unsqueeze(0), D, doclens, config=cfg)
+    except Exception:
+        return None
+
+
 def make_cpu_scorer():
     """Returns (kind, fn(Q [nq,d] fp32 torch, D [T,d] fp32 torch, doclens int64 torch) -> scores [n])."""
     import torch
+    fn = _reference_packed_scorer()
+    if fn is not None:
+        return "reference (colbert_score_packed imported from the reference checkout)", fn
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     try:
         import build_ref
@@ -82,7 +142,7 @@ def make_cpu_scorer():
             # colbert_score_packed, CPU branch (third_party/ColBERT/colbert/modeling/colbert.py:304,311):
             #   scores = D_packed @ Q.T ; ColBERT.segmented_maxsim(scores, D_lengths)
             return mod.segmented_maxsim_cpp((D @ Q.T).contiguous(), doclens)
-        return "reference", ref_fn
+        return "reference (its segmented_maxsim.cpp compiled in place + the D_packed @ Q.T it calls)", ref_fn
     from oracle import maxsim_oracle as O
 
     def port_fn(Q, D, doclens):
@@ -106,7 +166,9 @@ def cpu_reference_rate(args, target_seconds, steps=1, warmup=0):
         pass
     cores = torch.get_num_threads()
     g = torch.Generator().manual_seed(0)
-    Q = torch.nn.functional.normalize(torch.randn(args.nq, 128, generator=g), dim=-1).bfloat16().float()
+    n_q = 2
+    Qs = torch.nn.functional.normalize(torch.randn(n_q, args.nq, 128, generator=g), dim=-1).bfloat16().float()
+    Q = Qs[0]
 
     def make(n):
         D = torch.nn.functional.normalize(torch.randn(n * args.nd, 128, generator=g), dim=-1).bfloat16().float()
@@ -118,22 +180,24 @@ def cpu_reference_rate(args, target_seconds, steps=1, warmup=0):
     t0 = time.perf_counter()
     fn(Q, D, dl)
     t_probe = time.perf_counter() - t0
-    n_sample = int(min(max(n_probe, n_probe * target_seconds / max(t_probe, 1e-4)), 100_000, args.passages))
+    n_sample = int(min(max(n_probe, n_probe * target_seconds / max(t_probe * n_q, 1e-4)), 100_000, args.passages))
     D, dl = make(n_sample)
     for _ in range(warmup):
         fn(Q, D, dl)
     times = []
     for _ in range(max(steps, 1)):
         t0 = time.perf_counter()
-        s = fn(Q, D, dl)
-        s.topk(min(args.k, n_sample))
+        for qi in range(n_q):                       # the reference scores one query at a time (colbert.py:297)
+            s = fn(Qs[qi], D, dl)
+            s.topk(min(args.k, n_sample))
         times.append(time.perf_counter() - t0)
     t_step = sum(times) / len(times)
-    per_query_full = t_step * (args.passages / n_sample)
+    per_query_full = (t_step / n_q) * (args.passages / n_sample)
     return {"value": 1.0 / per_query_full, "unit": UNIT, "cores": cores, "kind": kind,
-            "sample": "1 query x %d of %d passages (Nq=%d, Nd=%d) exhaustive colbert_score_packed + topk, "
-                      "%.2f s per step, linearly extrapolated to the full corpus" %
-                      (n_sample, args.passages, args.nq, args.nd, t_step),
+            "sample_fraction": n_sample / args.passages, "sample_queries": n_q,
+            "sample": "%d queries x %d of %d passages (Nq=%d, Nd=%d) exhaustive colbert_score_packed + topk, "
+                      "%.2f s per step, per-query time linearly extrapolated to the full corpus" %
+                      (n_q, n_sample, args.passages, args.nq, args.nd, t_step),
             "ms_per_step": t_step * 1e3}
 
 
@@ -208,7 +272,7 @@ def cpu_plaid_rate(args, device, target_seconds=10.0):
         if t_total > target_seconds:
             break
     return {"value": done / t_total, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "reference",
-            "ms_per_query": 1e3 * t_total / done, "planted_passage_in_top_k": hits / done,
+            "ms_per_query": 1e3 * t_total / done, "recall_at_%d" % args.k: hits / done,
             "candidates_per_query": n_cand, "index": {"passages": n, "centroids": K, "nbits": nbits,
                                                       "build_seconds": t_build, "build_device": str(dev)},
             "sample": "%d queries (Nq=%d, first 32 tokens select cells) through the restated IndexScorer.rank "
@@ -227,10 +291,9 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": base["ms_per_step"],
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "FLMR MaxSim top-%d, %d passages x Nd=%d, Nq=%d, d=128 (bounded CPU sample)"
-                               % (args.k, args.passages, args.nd, args.nq),
-                   "n_passages": args.passages, "nd": args.nd, "nq": args.nq, "k": args.k},
-        "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "config": workload_config(args, max(1, args.gpus)),
+        "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample", "sample_fraction",
+                                              "sample_queries")},
         "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -303,6 +366,46 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+CHUNK = 20_000   # passages per generation chunk; chunk boundaries are GLOBAL so any rank can regenerate any passage
+
+
+def gen_chunk(ci, nd, dev):
+    """bf16 [CHUNK * nd, 128]: the tokens of global passages [ci * CHUNK, (ci + 1) * CHUNK), seeded by ci."""
+    import torch
+    g = torch.Generator(device=dev).manual_seed(1_000_003 * ci + 17)
+    x = torch.randn((CHUNK * nd, 128), device=dev, generator=g)
+    return torch.nn.functional.normalize(x, dim=-1).to(torch.bfloat16)
+
+
+def build_shard(p0, p1, nd, dev):
+    import torch
+    D = torch.empty(((p1 - p0) * nd, 128), dtype=torch.bfloat16, device=dev)
+    for ci in range(p0 // CHUNK, (p1 + CHUNK - 1) // CHUNK):
+        a, b = max(p0, ci * CHUNK), min(p1, (ci + 1) * CHUNK)
+        D[(a - p0) * nd:(b - p0) * nd] = gen_chunk(ci, nd, dev)[(a - ci * CHUNK) * nd:(b - ci * CHUNK) * nd]
+    return D
+
+
+def planted_queries(B, nq, nd, n_total, world, dev):
+    """Query b = Nq noisy copies (token/query cosine ~0.83) of the tokens of ONE corpus passage t_b that lives in
+    shard b mod world: a known positive per query, each in a different shard, so the MERGED global top-k of the
+    sharded search can be asserted at every N (and Recall@k reported).  The kernel's work is data-independent."""
+    import torch
+    targets, rows = [], []
+    for b in range(B):
+        r = b % world
+        s0, s1 = n_total * r // world, n_total * (r + 1) // world
+        t = s0 + (7919 * (b + 1)) % (s1 - s0)
+        ci = t // CHUNK
+        tok = gen_chunk(ci, nd, dev)[(t - ci * CHUNK) * nd:(t - ci * CHUNK + 1) * nd].float()
+        rows.append(tok[torch.arange(nq, device=dev) % nd])
+        targets.append(t)
+    g = torch.Generator(device=dev).manual_seed(12345)
+    Q = torch.stack(rows)
+    Q = torch.nn.functional.normalize(Q + 0.06 * torch.randn(Q.shape, device=dev, generator=g), dim=-1)
+    return Q, targets
+
+
 def run_ours(args):
     import numpy as np
     import torch
@@ -332,32 +435,25 @@ def run_ours(args):
     p0 = n_total * rank // world
     p1 = n_total * (rank + 1) // world
     n_local = p1 - p0
-    D = torch.empty((n_local * nd, 128), dtype=torch.bfloat16, device=dev)
-    chunk = 20_000
-    for c0 in range(0, n_local, chunk):
-        c1 = min(n_local, c0 + chunk)
-        g = torch.Generator(device=dev).manual_seed(1_000_003 * (p0 + c0) + 17)
-        x = torch.randn(((c1 - c0) * nd, 128), device=dev, generator=g)
-        D[c0 * nd:c1 * nd] = torch.nn.functional.normalize(x, dim=-1).to(torch.bfloat16)
-    del x
+    D = build_shard(p0, p1, nd, dev)
     corpus = R.FlatCorpus(D, np.full(n_local, nd, dtype=np.int32), device=dev, pid_base=p0)
-    gq = torch.Generator().manual_seed(12345)
-    Q_host = torch.nn.functional.normalize(torch.randn((B, nq, 128), generator=gq), dim=-1).pin_memory()
-    Q_dev = Q_host.to(dev).to(torch.bfloat16)
-    sharded = R.ShardedSearcher.from_corpus(corpus)
+    # queries with a planted positive each (rank 0 builds them, everyone receives the same bits)
+    if rank == 0:
+        Q32, targets = planted_queries(B, nq, nd, n_total, world, dev)
+    else:
+        Q32, targets = torch.empty((B, nq, 128), device=dev), [0] * B
+    if world > 1:
+        dist.broadcast(Q32, src=0)
+    Q_host = Q32.cpu().pin_memory()                  # fp32, pinned: what an encoder hands the Searcher
+    Q_dev = Q32.to(torch.bfloat16)
+    # THE product path: the reference-facing Searcher; with N ranks it keeps this rank's shard and merges the
+    # per-shard top-k with one all-gather
+    searcher = R.Searcher(index=corpus, shard_across_ranks=(world > 1))
     L = _cabi.lib()
+    qids = list(range(B))
 
     def step_device():
-        return sharded.search(Q_dev, k)
-
-    class _ShardedFacade(R.Searcher):
-        """Searcher whose tensor search goes through the sharded path (all-gather + merge)."""
-        def _search_tensors(self, Q, kk, filter_fn=None):
-            from ravqa_b200.maxsim import _prep_queries
-            return sharded.search(_prep_queries(corpus, Q), kk)
-
-    searcher = _ShardedFacade(index=corpus)
-    qids = list(range(B))
+        return searcher._search_tensors(Q_dev, k)
 
     def step_e2e():
         return searcher._search_all_Q(qids, Q_host, k, progress=False)
@@ -367,7 +463,7 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    def timed(fn, steps, warmup, profile=False):
+    def timed(fn, steps, warmup, profile=False, clocks=True):
         for _ in range(warmup):
             fn()
         barrier()
@@ -375,7 +471,7 @@ def run_ours(args):
             L.flmr_scan_kernel_stats(None, None, 1)
             L.flmr_set_profiling(1)
         L.flmr_launch_count(1)
-        sampler = ClockSampler(local_rank) if rank == 0 else None
+        sampler = ClockSampler(local_rank) if (rank == 0 and clocks) else None
         if sampler:
             sampler.start()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -387,7 +483,7 @@ def run_ours(args):
         barrier()
         wall_ms = (time.perf_counter() - t0) * 1e3
         dev_ms = e0.elapsed_time(e1)
-        clocks = sampler.stop() if sampler else None
+        clk = sampler.stop() if sampler else None
         launches = int(L.flmr_launch_count(0))
         scan_ms, scan_n = C.c_double(0), C.c_int64(0)
         if profile:
@@ -396,7 +492,7 @@ def run_ours(args):
         t = torch.tensor([dev_ms, wall_ms], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return {"dev_ms": t[0].item(), "wall_ms": t[1].item(), "clocks": clocks, "launches": launches,
+        return {"dev_ms": t[0].item(), "wall_ms": t[1].item(), "clocks": clk, "launches": launches,
                 "scan_ms": scan_ms.value, "scan_n": scan_n.value, "out": out}
 
     # device-resident timing (value) with per-launch scan-kernel events for the roofline
@@ -408,33 +504,65 @@ def run_ours(args):
     e2e_ms = max(r_e2e["dev_ms"], r_e2e["wall_ms"]) / args.steps
     e2e_value = B * 1e3 / e2e_ms
 
-    # sanity inside the bench: the fused result equals top-k of the all-scores path on this shard
+    # ---- parity inside the bench ----
+    # (1) the MERGED global ranking: every query's planted positive (each in a different shard) must come out
+    #     first, on every rank; Recall@k = share of queries whose positive is in the returned top-k
+    m_scores, m_pids = r_dev["out"]
+    pid_rows = m_pids.cpu().tolist()
+    if world > 1:
+        tg = torch.tensor(targets, dtype=torch.int64, device=dev)
+        dist.broadcast(tg, src=0)
+        targets = tg.tolist()
+    recall_1 = sum(int(row[0] == t) for row, t in zip(pid_rows, targets)) / B
+    recall_k = sum(int(t in row) for row, t in zip(pid_rows, targets)) / B
+    e2e_rows = [[p for p, _, _ in r_e2e["out"].todict()[q]] for q in qids]
+    e2e_same = e2e_rows == pid_rows
+    # (2) the fused result equals top-k of the all-scores path on this shard
     s_all = R.maxsim_scores(corpus, Q_dev[:1])
     ts, tp = R.maxsim_topk(corpus, Q_dev[:1], k)
     rs, rp = torch.sort(s_all, dim=1, descending=True, stable=True)
     self_check = bool(torch.equal(tp, rp[:, :k] + p0))
+    del s_all, rs, rp
 
-    # secondary measurement: the same kernel in its HBM-bound regime (one query of 32 tokens per corpus
-    # pass, the C1 query shape): algorithmic bytes / CUDA-event time of the scan launches
-    hbm_regime = None
-    if world == 1:
-        Qs = Q_dev[:1, :32].contiguous()
+    def scan_only(Qx, kk, reps):
+        """Average CUDA-event time of the scan launches of `reps` searches (warm)."""
         for _ in range(2):
-            R.maxsim_topk(corpus, Qs, k)
+            R.maxsim_topk(corpus, Qx, kk)
         torch.cuda.synchronize(dev)
         L.flmr_scan_kernel_stats(None, None, 1)
         L.flmr_set_profiling(1)
-        for _ in range(5):
-            R.maxsim_topk(corpus, Qs, k)
+        for _ in range(reps):
+            R.maxsim_topk(corpus, Qx, kk)
         torch.cuda.synchronize(dev)
         tot, cnt = C.c_double(0), C.c_int64(0)
         L.flmr_scan_kernel_stats(C.byref(tot), C.byref(cnt), 1)
         L.flmr_set_profiling(0)
-        if cnt.value:
-            ms = tot.value / cnt.value
-            gbs = corpus.info.n_tokens * 256.0 / (ms * 1e-3) / 1e9
+        return (tot.value / cnt.value) if cnt.value else None
+
+    peaks = load_peaks()
+    n_tok = float(corpus.info.n_tokens)
+    hbm_regime = b1 = None
+    if world == 1:
+        # the same kernel in its HBM-bound regime (one query of 32 tokens per corpus pass, the C1 query shape)
+        ms = scan_only(Q_dev[:1, :32].contiguous(), k, 5)
+        if ms:
+            gbs = n_tok * 256.0 / (ms * 1e-3) / 1e9
             hbm_regime = {"workload": "1 query x Nq=32 per corpus pass (HBM-bound regime of the same kernel)",
-                          "launch_ms": ms, "achieved": gbs, "unit": "GB/s", "queries_per_s": 1e3 / ms}
+                          "launch_ms": ms, "achieved": gbs, "unit": "GB/s", "queries_per_s": 1e3 / ms,
+                          "peak": peaks["hbm_gbs"], "frac": gbs / peaks["hbm_gbs"], "frac_of_8TBs": gbs / 8000.0}
+        # the north star's own shape: ONE query of Nq=320 per corpus pass (single-query latency path)
+        ms = scan_only(Q_dev[:1].contiguous(), k, 5)
+        if ms:
+            gbs = n_tok * 256.0 / (ms * 1e-3) / 1e9
+            tf = 2.0 * nq * 128 * n_tok / (ms * 1e-3) / 1e12
+            b1 = {"workload": "1 query x Nq=%d per corpus pass (batch 1: the shape the north star's HBM fraction "
+                              "is defined on)" % nq,
+                  "launch_ms": ms, "queries_per_s": 1e3 / ms,
+                  "hbm": {"achieved": gbs, "unit": "GB/s", "frac_of_measured_copy": gbs / peaks["hbm_gbs"],
+                          "hbm_frac_of_8TBs": gbs / 8000.0},
+                  "tensor": {"achieved": tf, "unit": "TFLOP/s (algorithmic: %d query rows)" % nq,
+                             "frac_of_burst": tf / peaks["bf16_burst"], "frac_of_sustained": tf / peaks["bf16_sustained"]},
+                  "query_rows_resident": ((nq + 31) // 32) * 32, "mma_rows_issued": ((nq + 127) // 128) * 128}
 
     # library GPU baseline (SURVEY.md §8d): the torch/cuBLAS composition the reference's GPU branch runs —
     # colbert_score (colbert.py:268-286): D_padded @ Q^T materialised as [n, Nd, Nq], padding fill, max over
@@ -473,75 +601,170 @@ def run_ours(args):
         except Exception as e:
             lib_gpu = {"value": None, "unit": UNIT, "kind": "error", "sample": repr(e)}
 
+    # ---- C2-shaped record (BASELINE.json configs[1]: PreFLMR ViT-B on OK-VQA's 112k-passage corpus): ragged
+    # passages, the full 832-row FLMR query (512 text + 320 vision rows, row-sliced over passes), k = max(Ks) = 100
+    c2 = None
+    if world == 1 and not args.no_c2:
+        try:
+            searcher = None
+            corpus.close()
+            del D
+            torch.cuda.empty_cache()
+            c2 = c2_record(args, dev, peaks)
+        except Exception as e:
+            c2 = {"value": None, "unit": UNIT, "kind": "error", "sample": repr(e)}
+
     if rank == 0:
-        peaks = load_peaks()
-        info = corpus.info
+        info_tokens = n_tok
         # dominant kernel = flmr_scan_kernel: one launch scans this rank's shard for the queries resident
         # in that pass.  Algorithmic work per launch (DESIGN.md "Roofline"):
         q_per_launch = max(1, 20 // ((nq + 31) // 32)) if (nq + 31) // 32 <= 20 else 1
         q_per_launch = min(q_per_launch, B)
-        flops_launch = 2.0 * q_per_launch * nq * 128 * float(info.n_tokens)
-        bytes_launch = float(info.n_tokens) * 256.0
+        flops_launch = 2.0 * q_per_launch * nq * 128 * info_tokens
+        bytes_launch = info_tokens * 256.0
         scan_avg_ms = r_dev["scan_ms"] / max(r_dev["scan_n"], 1)
         ach_tf = flops_launch / (scan_avg_ms * 1e-3) / 1e12 if scan_avg_ms > 0 else 0.0
         ach_gbs = bytes_launch / (scan_avg_ms * 1e-3) / 1e9 if scan_avg_ms > 0 else 0.0
-        # DRAM traffic of one launch from the committed `ncu --set full` capture at this exact size
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
-        if os.path.exists(tpath) and world == 1 and (n_total, nd, nq) == (1_000_000, 180, 320) and q_per_launch == 2:
-            with open(tpath) as f:
-                traffic = json.load(f).get("traffic_bytes_per_launch")
+        # DRAM traffic of one launch from the committed `ncu --set full` capture at this exact size; reported
+        # only while the kernel sources still hash to what was captured (else null: stale)
+        traffic = traffic_src = None
+        sha = kernel_source_sha()
+        for tname in ("r02_traffic.json", "r01_traffic.json"):
+            tpath = os.path.join(ROOT, "profiles", tname)
+            if os.path.exists(tpath) and world == 1 and (n_total, nd, nq) == (1_000_000, 180, 320):
+                with open(tpath) as f:
+                    tj = json.load(f)
+                if tj.get("kernel_source_sha") == sha and tj.get("queries_per_launch", 2) == q_per_launch:
+                    traffic = tj.get("traffic_bytes_per_launch")
+                    traffic_src = "profiles/%s (ncu --set full: dram__bytes_read.sum + dram__bytes_write.sum per launch; kernel sources %s)" % (tname, sha)
+                    break
         roofline = {
             "bound": "tensor", "achieved": ach_tf, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
             "frac": ach_tf / peaks["bf16_sustained"], "traffic": traffic,
-            "traffic_source": "profiles/r01_ncu_scan_kernel.md (dram__bytes_read.sum + dram__bytes_write.sum, bytes per launch)" if traffic else None,
+            "traffic_source": traffic_src, "kernel_source_sha": sha,
             "peak_source": peaks["source"] + " (sustained cuBLAS bf16: kernel timed inside a long step)",
             "kernel": "flmr_scan_kernel", "launch_ms": scan_avg_ms, "launches_timed": r_dev["scan_n"],
             "scan_share_of_step": r_dev["scan_ms"] / r_dev["dev_ms"] if r_dev["dev_ms"] > 0 else None,
             "hbm": {"achieved": ach_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                     "frac": ach_gbs / peaks["hbm_gbs"], "frac_of_8TBs": ach_gbs / 8000.0,
                     "algorithmic_bytes_per_launch": bytes_launch},
-            "algorithmic_flops_per_launch": flops_launch,
+            "algorithmic_flops_per_launch": flops_launch, "queries_per_launch": q_per_launch,
         }
         if hbm_regime:
-            hbm_regime.update(peak=peaks["hbm_gbs"], frac=hbm_regime["achieved"] / peaks["hbm_gbs"],
-                              frac_of_8TBs=hbm_regime["achieved"] / 8000.0)
             roofline["hbm_bound_regime"] = hbm_regime
+        if b1:
+            roofline["b1"] = b1
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "FLMR MaxSim top-%d: %d passages x Nd=%d, Nq=%d, d=128, batch %d queries/step"
-                                   % (k, n_total, nd, nq, B),
-                       "n_passages": n_total, "nd": nd, "nq": nq, "dim": 128, "k": k, "batch": B,
-                       "parallelism": "passage-shard x%d + allgather(top-k)" % world,
-                       "l2": "inputs larger than L2 (%.1f GB of passage tokens per GPU per pass)"
-                             % (info.n_tokens * 256 / 1e9)},
+            "config": workload_config(args, world),
             "clocks": r_dev["clocks"],
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": B * nq * 128 * 4, "d2h_bytes_per_step": B * k * 12,
                     "api": "Searcher._search_all_Q(queries, Q_host_fp32_pinned, k) -> Ranking"},
             "gpu_launches": r_dev["launches"],
             "roofline": roofline,
+            "recall_at_%d" % k: recall_k, "recall_at_1": recall_1,
+            "parity": {"merged_top1_is_the_planted_positive": recall_1 == 1.0,
+                       "positives": "one per query, query b's in shard b mod %d" % world,
+                       "e2e_ranking_equals_device_ranking": e2e_same,
+                       "fused_topk_equals_sorted_scores_on_local_shard": self_check},
             "self_check_fused_topk_equals_sorted_scores": self_check,
         }
         if world == 1 and not args.no_cpu_baseline:
             try:
                 base = cpu_reference_rate(args, args.cpu_seconds)
-                line["cpu_baseline"] = {kk: base[kk] for kk in ("value", "unit", "cores", "kind", "sample")}
+                line["cpu_baseline"] = {kk: base[kk] for kk in ("value", "unit", "cores", "kind", "sample",
+                                                                "sample_fraction", "sample_queries")}
             except Exception as e:  # the baseline must never take the bench line down
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": None, "kind": "error", "sample": repr(e)}
         if lib_gpu:
             line["library_gpu_baseline"] = lib_gpu
+        if c2:
+            line["c2"] = c2
         if world == 1 and not args.no_cpu_baseline and not args.no_plaid_baseline:
             try:
                 line["cpu_baseline_plaid"] = cpu_plaid_rate(args, "cuda:%d" % local_rank)
             except Exception as e:
                 line["cpu_baseline_plaid"] = {"value": None, "unit": UNIT, "kind": "error", "sample": repr(e)}
         print(json.dumps(line), flush=True)
+    ok = (recall_1 == 1.0) and self_check and e2e_same
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    if not ok:
+        raise SystemExit("bench parity check failed: recall@1=%.3f self_check=%s e2e_same=%s"
+                         % (recall_1, self_check, e2e_same))
+
+
+def c2_record(args, dev, peaks):
+    """One GPU, C2 shape: `--c2-passages` ragged passages (90..180 tokens, the OK-VQA GoogleSearch corpus at
+    max_decoder_source_length-ish lengths), 16 queries of Nq = 832 rows, k = 100 (max(Ks),
+    FLMR_base_preload_vision_features.jsonnet:141).  Own roofline: FLOPs = 2 * B * 832 * 128 * tokens per step
+    over the summed CUDA-event time of the step's scan launches."""
+    import ctypes as C
+    import numpy as np
+    import torch
+    import ravqa_b200 as R
+    from ravqa_b200 import _cabi
+    L = _cabi.lib()
+    n, nq, k, B = args.c2_passages, 832, 100, 16
+    g = torch.Generator().manual_seed(2)
+    doclens = torch.randint(90, 181, (n,), generator=g)
+    n_tok = int(doclens.sum())
+    D = torch.empty((n_tok, 128), dtype=torch.bfloat16, device=dev)
+    gd = torch.Generator(device=dev).manual_seed(3)
+    for a in range(0, n_tok, 1 << 22):
+        b = min(n_tok, a + (1 << 22))
+        D[a:b] = torch.nn.functional.normalize(torch.randn((b - a, 128), device=dev, generator=gd), dim=-1).bfloat16()
+    off = torch.cat([torch.zeros(1, dtype=torch.long), doclens.cumsum(0)])
+    targets = [(104_729 * (b + 1)) % n for b in range(B)]
+    rows = []
+    for t in targets:                               # planted positive per query (as in the headline workload)
+        tok = D[off[t]:off[t + 1]].float()
+        rows.append(tok[torch.arange(nq, device=dev) % tok.size(0)])
+    Q = torch.stack(rows)
+    Q = torch.nn.functional.normalize(Q + 0.06 * torch.randn(Q.shape, device=dev, generator=gd), dim=-1).bfloat16()
+    corpus = R.FlatCorpus(D, doclens.numpy().astype(np.int32), device=dev)
+    del D
+    searcher = R.Searcher(index=corpus)
+    steps, warmup = max(3, min(args.steps, 10)), 3
+    for _ in range(warmup):
+        searcher._search_tensors(Q, k)
+    torch.cuda.synchronize(dev)
+    L.flmr_scan_kernel_stats(None, None, 1)
+    L.flmr_set_profiling(1)
+    L.flmr_launch_count(1)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        s, p = searcher._search_tensors(Q, k)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    launches = int(L.flmr_launch_count(0))
+    tot, cnt = C.c_double(0), C.c_int64(0)
+    L.flmr_scan_kernel_stats(C.byref(tot), C.byref(cnt), 1)
+    L.flmr_set_profiling(0)
+    ms_step = e0.elapsed_time(e1) / steps
+    scan_ms_step = tot.value / steps
+    flops_step = 2.0 * B * nq * 128 * n_tok
+    tf = flops_step / (scan_ms_step * 1e-3) / 1e12
+    rows_out = p.cpu().tolist()
+    rec = {"workload": "C2 shape: %d ragged passages (90..180 tokens, %d tokens), %d queries x Nq=%d, k=%d"
+                       % (n, n_tok, B, nq, k),
+           "value": B * 1e3 / ms_step, "unit": UNIT, "ms_per_step": ms_step, "steps": steps, "warmup": warmup,
+           "scan_launches_per_step": cnt.value // steps, "gpu_launches_per_step": launches // steps,
+           "recall_at_1": sum(int(r[0] == t) for r, t in zip(rows_out, targets)) / B,
+           "recall_at_100": sum(int(t in r) for r, t in zip(rows_out, targets)) / B,
+           "roofline": {"bound": "tensor", "achieved": tf, "unit": "TFLOP/s", "peak": peaks["bf16_burst"],
+                        "frac": tf / peaks["bf16_burst"],
+                        "peak_source": peaks["source"] + " (burst cuBLAS bf16: a 50 ms step, not power-limited)",
+                        "scan_ms_per_step": scan_ms_step, "scan_share_of_step": scan_ms_step / ms_step,
+                        "algorithmic_flops_per_step": flops_step,
+                        "hbm_gbs": (cnt.value // steps) * n_tok * 256.0 / (scan_ms_step * 1e-3) / 1e9}}
+    corpus.close()
+    return rec
 
 
 def main():

@@ -18,9 +18,17 @@ def test_reference_arm_json_contract():
                 "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e", "gpu_launches"):
         assert key in line, key
     assert line["impl"] == "reference" and line["value"] > 0 and line["higher_is_better"] is True
-    assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] >= 1
+    assert line["cpu_baseline"]["kind"].split(" ")[0] in ("reference", "port") and line["cpu_baseline"]["cores"] >= 1
+    assert line["cpu_baseline"]["sample_queries"] >= 2 and 0 < line["cpu_baseline"]["sample_fraction"] <= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
     assert "workload" in line["config"]
+    # both arms describe the workload with the SAME config object (one function builds it)
+    sys.path.insert(0, ROOT)
+    import types
+
+    import bench
+    args = types.SimpleNamespace(passages=3000, nd=180, nq=320, batch=16, k=5)
+    assert line["config"] == bench.workload_config(args, 1)
 
 
 def test_reference_arm_other_ranks_exit_quietly():
@@ -43,5 +51,5 @@ def test_plaid_cpu_baseline_leg_runs_on_a_small_sample():
     args = types.SimpleNamespace(plaid_passages=1000, nd=60, nq=64, k=5, plaid_ndocs=16)
     out = bench.cpu_plaid_rate(args, "cpu", target_seconds=1.0)
     assert out["kind"] == "reference" and out["value"] > 0 and out["cores"] >= 1
-    assert out["planted_passage_in_top_k"] >= 0.9          # clustered data: PLAID finds the planted passage
+    assert out["recall_at_5"] >= 0.9          # clustered data: PLAID finds the planted passage
     assert min(out["candidates_per_query"]) >= 16 and "NOT extrapolated" in out["sample"]
