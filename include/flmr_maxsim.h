@@ -74,6 +74,7 @@ extern "C" {
 
 typedef struct flmr_corpus flmr_corpus_t;       /* resident passage-token shard            */
 typedef struct flmr_workspace flmr_workspace_t; /* per-caller scratch (candidates, Q pad)  */
+typedef struct flmr_comm flmr_comm_t;           /* this rank's end of the shard exchange   */
 
 typedef struct flmr_corpus_info {
   int64_t n_passages;     /* passages in this shard                                           */
@@ -148,6 +149,32 @@ int flmr_maxsim_topk(const flmr_corpus_t* corpus, flmr_workspace_t* ws, const vo
 int flmr_topk_merge(const float* d_in_scores, const int64_t* d_in_pids, int n_lists, int n_queries,
                     int k_in, int k_out, float* d_out_scores, int64_t* d_out_pids, int device,
                     void* stream);
+
+/*
+ * The sharded search at the C boundary (the reference has no counterpart: under DDP every rank
+ * repeats the whole CPU search, src/executors/FLMR_executor.py:778-781).  Each rank holds a contiguous passage
+ * shard (flmr_corpus_create with its pid_base); ONE exchange step — an NCCL all-gather of every rank's [B, k]
+ * (score, pid) lists — then the merge kernel, all asynchronous on `stream`, no host synchronisation, so a
+ * non-Python host can run the multi-GPU path.  NCCL is dlopen'ed at run time (the process's own copy if it has
+ * loaded one); without it these calls return FLMR_ERR_UNSUPPORTED.
+ *
+ *   flmr_comm_unique_id   rank 0 obtains the 128-byte NCCL id and hands it to the other ranks (any host channel)
+ *   flmr_comm_create      collective: ncclCommInitRank on `device`
+ *   flmr_comm_adopt       wrap an existing ncclComm_t (not destroyed with the handle)
+ *   flmr_topk_exchange    all-gather + merge of lists the caller already has (d_scores / d_pids [n_queries, k_in],
+ *                         entries with pid < 0 ignored) -> [n_queries, k_out] on EVERY rank
+ *   flmr_maxsim_topk_sharded   flmr_maxsim_topk on this rank's shard + flmr_topk_exchange, one call
+ */
+int flmr_comm_unique_id(void* out_id_128_bytes);
+int flmr_comm_create(const void* id_128_bytes, int rank, int world_size, int device, flmr_comm_t** out);
+int flmr_comm_adopt(void* nccl_comm, int device, flmr_comm_t** out);
+int flmr_comm_destroy(flmr_comm_t* comm);
+int flmr_comm_info(const flmr_comm_t* comm, int* rank, int* world_size);
+int flmr_topk_exchange(flmr_comm_t* comm, const float* d_scores, const int64_t* d_pids, int n_queries, int k_in,
+                       int k_out, float* d_out_scores, int64_t* d_out_pids, void* stream);
+int flmr_maxsim_topk_sharded(const flmr_corpus_t* corpus, flmr_workspace_t* ws, flmr_comm_t* comm, const void* d_q,
+                             int n_queries, int nq, int k, unsigned flags, float* d_out_scores,
+                             int64_t* d_out_pids, void* stream);
 
 /*
  * Top-k of dense score rows for k beyond FLMR_MAX_K (Searcher.dense_search accepts any k,

@@ -68,25 +68,44 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 }
 
 // Bounded wait: a protocol bug must surface as a trapped launch, never as a hung GPU box.
-// `status` receives `code` before the trap so the host can say which role starved.  The spinning
-// path is kept out of line so the hot loops stay small (instruction-cache footprint).
+// `status` receives `code` before the trap so the host can say which role starved.
+//
+// The polling loop is written in PTX so that one iteration is the try_wait itself plus four instructions: the
+// round-1 C++ loop compiled to 15 instructions per iteration, and with waits this fine-grained (a warp is woken
+// by every partial arrival on its barrier) the polling iterations were 25 % of all warp instructions the scan
+// kernel executed (profiles/r01 source page).  The watchdog reads the timer once per kSpinBlock failed polls.
+constexpr uint32_t kSpinBlock = 4096;
+__device__ __forceinline__ uint32_t mbar_poll_block(uint32_t bar, uint32_t parity) {
+  uint32_t n;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .u32 c;\n\t"
+      "mov.u32 c, 0;\n"
+      "FLMR_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "@p bra FLMR_DONE;\n\t"
+      "add.u32 c, c, 1;\n\t"
+      "setp.lt.u32 p, c, %4;\n\t"
+      "@p bra FLMR_WAIT;\n"
+      "FLMR_DONE:\n\t"
+      "mov.u32 %0, c;\n\t}"
+      : "=r"(n)
+      : "r"(bar), "r"(parity), "r"(0x989680u), "r"(kSpinBlock)
+      : "memory");
+  return n;   // < kSpinBlock: the phase completed
+}
 __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity, int* status, int code) {
   // 20 s of polling = a protocol bug, not a slow wait (time slicing, a sanitizer or a debugger can stretch a
   // legitimate wait to seconds; the longest real wait of a scan is one tile, microseconds)
   constexpr uint64_t timeout_ns = 20000000000ull;
-  uint32_t spins = 0;
   uint64_t t0 = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if (++spins == 64u) {
-      spins = 0;
-      const uint64_t now = global_timer_ns();
-      if (t0 == 0) {
-        t0 = now;
-      } else if (now - t0 > timeout_ns) {
-        if (status) *reinterpret_cast<volatile int*>(status) = code;
-        __threadfence_system();
-        __trap();
-      }
+  while (mbar_poll_block(bar, parity) >= kSpinBlock) {
+    const uint64_t now = global_timer_ns();
+    if (t0 == 0) {
+      t0 = now;
+    } else if (now - t0 > timeout_ns) {
+      if (status) *reinterpret_cast<volatile int*>(status) = code;
+      __threadfence_system();
+      __trap();
     }
   }
 }

@@ -9,6 +9,7 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
 #include <algorithm>
 #include <cmath>
@@ -496,7 +497,75 @@ struct flmr_workspace {
   int dbg_mode = 0, dbg_lane_rbq = 4;  // -DFLMR_DEBUG builds: FLMR_DEBUG_MODE / FLMR_LANE_RBQ, read once at creation
 };
 
+// NCCL is resolved at RUN time (dlopen): the library has no link dependency on it, loads on a box without
+// NCCL, and shares the libnccl the host process already loaded (torch ships its own) when there is one.
+struct NcclApi {
+  void* handle = nullptr;
+  int (*GetUniqueId)(void*) = nullptr;
+  int (*CommInitRank)(void**, int, /* ncclUniqueId by value: 128 bytes */ struct NcclId, int) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  int (*CommCount)(void*, int*) = nullptr;
+  int (*CommUserRank)(void*, int*) = nullptr;
+};
+struct NcclId {
+  char internal[128];
+};
+
+struct flmr_comm {
+  void* nccl = nullptr;   // ncclComm_t
+  int rank = 0, world = 1, device = 0;
+  bool owned = false;     // created by flmr_comm_create (destroyed with the handle) vs adopted
+  // exchange buffers, grown on demand: this rank's [B, k] lists and everybody's [world, B, k]
+  float* d_send_s = nullptr;
+  int64_t* d_send_p = nullptr;
+  float* d_recv_s = nullptr;
+  int64_t* d_recv_p = nullptr;
+  int64_t capacity = 0;   // entries (B * k) the send buffers hold
+};
+
 namespace {
+
+int load_nccl(const NcclApi** out) {
+  static NcclApi api;
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lock(mu);
+  if (!api.handle) {
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);   // the copy the process already uses, if any
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) return fail(FLMR_ERR_UNSUPPORTED, "NCCL is not available (dlopen libnccl.so.2: %s)", dlerror());
+    NcclApi a;
+    a.handle = h;
+    a.GetUniqueId = reinterpret_cast<decltype(a.GetUniqueId)>(dlsym(h, "ncclGetUniqueId"));
+    a.CommInitRank = reinterpret_cast<decltype(a.CommInitRank)>(dlsym(h, "ncclCommInitRank"));
+    a.CommDestroy = reinterpret_cast<decltype(a.CommDestroy)>(dlsym(h, "ncclCommDestroy"));
+    a.AllGather = reinterpret_cast<decltype(a.AllGather)>(dlsym(h, "ncclAllGather"));
+    a.GroupStart = reinterpret_cast<decltype(a.GroupStart)>(dlsym(h, "ncclGroupStart"));
+    a.GroupEnd = reinterpret_cast<decltype(a.GroupEnd)>(dlsym(h, "ncclGroupEnd"));
+    a.GetErrorString = reinterpret_cast<decltype(a.GetErrorString)>(dlsym(h, "ncclGetErrorString"));
+    a.CommCount = reinterpret_cast<decltype(a.CommCount)>(dlsym(h, "ncclCommCount"));
+    a.CommUserRank = reinterpret_cast<decltype(a.CommUserRank)>(dlsym(h, "ncclCommUserRank"));
+    if (!a.GetUniqueId || !a.CommInitRank || !a.CommDestroy || !a.AllGather || !a.GroupStart || !a.GroupEnd ||
+        !a.GetErrorString || !a.CommCount || !a.CommUserRank)
+      return fail(FLMR_ERR_UNSUPPORTED, "libnccl.so.2 lacks an expected entry point");
+    api = a;
+  }
+  *out = &api;
+  return FLMR_OK;
+}
+
+#define FLMR_NCCL(api, expr)                                                                          \
+  do {                                                                                                \
+    int r__ = (expr);                                                                                 \
+    if (r__ != 0)                                                                                     \
+      return fail(FLMR_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, (api)->GetErrorString(r__), __FILE__, __LINE__); \
+  } while (0)
+
+constexpr int kNcclInt64 = 4, kNcclFloat32 = 7;   // ncclDataType_t values (nccl.h: ncclInt64 = 4, ncclFloat32 = 7)
 
 thread_local bool g_profiling = false;
 struct EventPair {
@@ -1290,6 +1359,147 @@ int flmr_debug_plan_passes(int n_queries, int nq, int32_t* out_plan, int capacit
     }
   }
   return FLMR_OK;
+}
+
+int flmr_comm_unique_id(void* out_id_128_bytes) {
+  if (!out_id_128_bytes) return fail(FLMR_ERR_INVALID_ARG, "null argument");
+  const NcclApi* api = nullptr;
+  if (int rc = load_nccl(&api)) return rc;
+  FLMR_NCCL(api, api->GetUniqueId(out_id_128_bytes));
+  return FLMR_OK;
+}
+
+int flmr_comm_create(const void* id_128_bytes, int rank, int world_size, int device, flmr_comm_t** out) {
+  if (!id_128_bytes || !out) return fail(FLMR_ERR_INVALID_ARG, "null argument");
+  *out = nullptr;
+  if (world_size < 1 || rank < 0 || rank >= world_size)
+    return fail(FLMR_ERR_INVALID_ARG, "bad rank %d / world size %d", rank, world_size);
+  const NcclApi* api = nullptr;
+  if (int rc = load_nccl(&api)) return rc;
+  DeviceGuard guard(device);
+  if (!guard.ok) return fail(FLMR_ERR_CUDA, "cudaSetDevice(%d) failed", device);
+  flmr_comm* c = new (std::nothrow) flmr_comm();
+  if (!c) return fail(FLMR_ERR_OOM, "host allocation failed");
+  NcclId id;
+  memcpy(id.internal, id_128_bytes, sizeof id.internal);
+  const int r = api->CommInitRank(&c->nccl, world_size, id, rank);
+  if (r != 0) {
+    delete c;
+    return fail(FLMR_ERR_CUDA, "ncclCommInitRank failed: %s", api->GetErrorString(r));
+  }
+  c->rank = rank;
+  c->world = world_size;
+  c->device = device;
+  c->owned = true;
+  *out = c;
+  return FLMR_OK;
+}
+
+int flmr_comm_adopt(void* nccl_comm, int device, flmr_comm_t** out) {
+  if (!nccl_comm || !out) return fail(FLMR_ERR_INVALID_ARG, "null argument");
+  *out = nullptr;
+  const NcclApi* api = nullptr;
+  if (int rc = load_nccl(&api)) return rc;
+  flmr_comm* c = new (std::nothrow) flmr_comm();
+  if (!c) return fail(FLMR_ERR_OOM, "host allocation failed");
+  c->nccl = nccl_comm;
+  c->device = device;
+  int r = api->CommCount(nccl_comm, &c->world);
+  if (r == 0) r = api->CommUserRank(nccl_comm, &c->rank);
+  if (r != 0) {
+    delete c;
+    return fail(FLMR_ERR_CUDA, "ncclCommCount / ncclCommUserRank failed: %s", api->GetErrorString(r));
+  }
+  *out = c;
+  return FLMR_OK;
+}
+
+int flmr_comm_destroy(flmr_comm_t* c) {
+  if (!c) return FLMR_OK;
+  DeviceGuard guard(c->device);
+  cudaFree(c->d_send_s);
+  cudaFree(c->d_send_p);
+  cudaFree(c->d_recv_s);
+  cudaFree(c->d_recv_p);
+  if (c->owned && c->nccl) {
+    const NcclApi* api = nullptr;
+    if (load_nccl(&api) == FLMR_OK) api->CommDestroy(c->nccl);
+  }
+  delete c;
+  return FLMR_OK;
+}
+
+int flmr_comm_info(const flmr_comm_t* c, int* rank, int* world_size) {
+  if (!c) return fail(FLMR_ERR_INVALID_ARG, "null argument");
+  if (rank) *rank = c->rank;
+  if (world_size) *world_size = c->world;
+  return FLMR_OK;
+}
+
+int flmr_topk_exchange(flmr_comm_t* c, const float* d_scores, const int64_t* d_pids, int n_queries, int k_in,
+                       int k_out, float* d_out_scores, int64_t* d_out_pids, void* stream) {
+  if (!c || !d_scores || !d_pids || !d_out_scores || !d_out_pids) return fail(FLMR_ERR_INVALID_ARG, "null argument");
+  if (n_queries < 0 || k_in < 1 || k_out < 1 || k_out > kMaxK)
+    return fail(FLMR_ERR_INVALID_ARG, "bad shape n_queries=%d k_in=%d k_out=%d", n_queries, k_in, k_out);
+  if (static_cast<int64_t>(c->world) * k_in > kMergeThreads * kMergePer)
+    return fail(FLMR_ERR_UNSUPPORTED, "world*k_in = %lld exceeds merge capacity %d", (long long)c->world * k_in,
+                kMergeThreads * kMergePer);
+  if (n_queries == 0) return FLMR_OK;
+  const NcclApi* api = nullptr;
+  if (int rc = load_nccl(&api)) return rc;
+  DeviceGuard guard(c->device);
+  if (!guard.ok) return fail(FLMR_ERR_CUDA, "cudaSetDevice(%d) failed", c->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int64_t n = static_cast<int64_t>(n_queries) * k_in;
+  if (c->capacity < n) {   // (grown only when a call brings more entries than any before: not on the steady path)
+    cudaFree(c->d_recv_s);
+    cudaFree(c->d_recv_p);
+    c->d_recv_s = nullptr;
+    c->d_recv_p = nullptr;
+    c->capacity = 0;
+    FLMR_CUDA(cudaMalloc(reinterpret_cast<void**>(&c->d_recv_s), static_cast<size_t>(n) * c->world * sizeof(float)));
+    FLMR_CUDA(cudaMalloc(reinterpret_cast<void**>(&c->d_recv_p), static_cast<size_t>(n) * c->world * sizeof(int64_t)));
+    c->capacity = n;
+  }
+  // one exchange step: both all-gathers in ONE NCCL group (a single fused launch on the wire), then the merge
+  FLMR_NCCL(api, api->GroupStart());
+  int r1 = api->AllGather(d_scores, c->d_recv_s, static_cast<size_t>(n), kNcclFloat32, c->nccl, st);
+  int r2 = api->AllGather(d_pids, c->d_recv_p, static_cast<size_t>(n), kNcclInt64, c->nccl, st);
+  FLMR_NCCL(api, api->GroupEnd());
+  if (r1 != 0 || r2 != 0)
+    return fail(FLMR_ERR_CUDA, "ncclAllGather failed: %s", api->GetErrorString(r1 ? r1 : r2));
+  flmr_merge_kernel<<<n_queries, kMergeThreads, 0, st>>>(nullptr, c->d_recv_s, c->d_recv_p, c->world, n_queries,
+                                                        k_in, k_out, 0, d_out_scores, d_out_pids);
+  FLMR_CUDA(cudaGetLastError());
+  ++g_launches;
+  return FLMR_OK;
+}
+
+int flmr_maxsim_topk_sharded(const flmr_corpus_t* corpus, flmr_workspace_t* ws, flmr_comm_t* comm, const void* d_q,
+                             int n_queries, int nq, int k, unsigned flags, float* d_out_scores,
+                             int64_t* d_out_pids, void* stream) {
+  if (!comm) return fail(FLMR_ERR_INVALID_ARG, "comm is null");
+  if (!d_out_scores || !d_out_pids) return fail(FLMR_ERR_INVALID_ARG, "output pointer is null");
+  if (k < 1 || k > kMaxK) return fail(FLMR_ERR_INVALID_ARG, "k=%d outside [1, %d]", k, kMaxK);
+  if (corpus && corpus->device != comm->device)
+    return fail(FLMR_ERR_INVALID_ARG, "corpus on device %d, communicator on device %d", corpus->device, comm->device);
+  if (n_queries <= 0) return n_queries == 0 ? FLMR_OK : fail(FLMR_ERR_INVALID_ARG, "bad n_queries=%d", n_queries);
+  DeviceGuard guard(comm->device);
+  if (!guard.ok) return fail(FLMR_ERR_CUDA, "cudaSetDevice(%d) failed", comm->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int64_t n = static_cast<int64_t>(n_queries) * k;
+  if (comm->capacity < n || !comm->d_send_s) {
+    cudaFree(comm->d_send_s);
+    cudaFree(comm->d_send_p);
+    comm->d_send_s = nullptr;
+    comm->d_send_p = nullptr;
+    FLMR_CUDA(cudaMalloc(reinterpret_cast<void**>(&comm->d_send_s), static_cast<size_t>(n) * sizeof(float)));
+    FLMR_CUDA(cudaMalloc(reinterpret_cast<void**>(&comm->d_send_p), static_cast<size_t>(n) * sizeof(int64_t)));
+  }
+  // this rank's shard (the fused scan fills short lists with (-inf, -1), which the merge ignores)
+  if (int rc = run_search(corpus, ws, d_q, n_queries, nq, flags, k, nullptr, comm->d_send_s, comm->d_send_p, st))
+    return rc;
+  return flmr_topk_exchange(comm, comm->d_send_s, comm->d_send_p, n_queries, k, k, d_out_scores, d_out_pids, stream);
 }
 
 int64_t flmr_launch_count(int reset) {

@@ -151,6 +151,7 @@ class Searcher:
         self.encode_fn = encode_fn
         self.query_batch = int(query_batch)
         self._sharded = None
+        self._nccl = None
         self.index_config = None
         run_cfg = active_run_config(config)
         if isinstance(index, FlatCorpus):
@@ -181,13 +182,19 @@ class Searcher:
         except Exception:          # foreign config type with a different constructor: keep what was given
             self.config = config
         if shard_across_ranks:
+            import torch.distributed as dist
             from .maxsim import topk_merge
-            from .sharded import ShardedSearcher
+            from .sharded import NcclExchange, ShardedSearcher
             self._sharded = ShardedSearcher(None, lambda s, p, k: topk_merge(s, p, k), group)
+            self._group = group
+            self._want_nccl = dist.get_backend(group) == "nccl"
         if self.corpus is not None:
             self.device = self.corpus.device
         else:
             self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if self._sharded is not None and self._want_nccl:
+            from .sharded import NcclExchange
+            self._nccl = NcclExchange(self.device, self._group)       # collective: every rank constructs it
         self._relu = False
 
     # -- reference-compatible surface ------------------------------------------------------------
@@ -273,12 +280,25 @@ class Searcher:
         if filter_fn is not None and corpus is not None:
             all_pids = torch.arange(corpus.n_passages, device=corpus.device) + corpus.pid_base
             keep = torch.as_tensor(filter_fn(all_pids), device=corpus.device).long() - corpus.pid_base
+        if self._sharded is not None and int(k) > _cabi.MAX_K:
+            raise ValueError("sharded search merges at most k=%d results per query" % _cabi.MAX_K)
+        if self._nccl is not None and keep is None and corpus is not None:
+            # the C-level sharded search: scan + one grouped all-gather + merge per call, no torch glue
+            outs = [self._nccl.search(corpus, Q[b0:b0 + self.query_batch], int(k), relu=self._relu)
+                    for b0 in range(0, Q.size(0), self.query_batch)]
+            s, p = torch.cat([o[0] for o in outs]), torch.cat([o[1] for o in outs])
+            n_valid = int((p[0] >= 0).sum()) if p.numel() else 0
+            return s[:, :n_valid], p[:, :n_valid]
         s, p = self._local_topk(Q, int(k), keep)
         if self._sharded is not None:
             k_merge = int(k)
-            if k_merge > _cabi.MAX_K:
-                raise ValueError("sharded search merges at most k=%d results per query" % _cabi.MAX_K)
-            s, p = self._sharded.exchange(s.to(self.device), p.to(self.device), k_merge)
+            if s.size(1) < k_merge:                      # short shard: pad with empty entries
+                s = torch.cat([s, s.new_full((s.size(0), k_merge - s.size(1)), float("-inf"))], dim=1)
+                p = torch.cat([p, p.new_full((p.size(0), k_merge - p.size(1)), -1)], dim=1)
+            if self._nccl is not None:
+                s, p = self._nccl.exchange(s, p, k_merge)
+            else:
+                s, p = self._sharded.exchange(s.to(self.device), p.to(self.device), k_merge)
             n_valid = int((p[0] >= 0).sum()) if p.numel() else 0    # same for every query: min(k, candidates)
             s, p = s[:, :n_valid], p[:, :n_valid]
         return s, p

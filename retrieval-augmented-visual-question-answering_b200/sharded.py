@@ -29,6 +29,77 @@ def shard_ranges(doclens: Sequence[int], world_size: int) -> List[Tuple[int, int
     return [(bounds[r], bounds[r + 1]) for r in range(world_size)]
 
 
+class NcclExchange:
+    """This rank's end of the C-level exchange (``flmr_comm_*`` / ``flmr_maxsim_topk_sharded`` /
+    ``flmr_topk_exchange``): the library's own NCCL communicator, created from an id that rank 0 obtains and
+    ``torch.distributed`` broadcasts once.  Per search: the fused scan, ONE grouped all-gather and the merge
+    kernel, all enqueued by one C call on the current stream — no tensor packing or casting on the way."""
+
+    def __init__(self, device: torch.device, group=None):
+        import ctypes as C
+        from . import _cabi
+        L = _cabi.lib()
+        self.device = device
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        uid = torch.zeros(128, dtype=torch.uint8)
+        if self.rank == 0:
+            buf = (C.c_char * 128)()
+            _cabi.check(L.flmr_comm_unique_id(C.cast(buf, C.c_void_p)))
+            uid = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).clone()
+        backend = dist.get_backend(group)
+        uid = uid.to(device) if backend == "nccl" else uid
+        dist.broadcast(uid, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        raw = bytes(uid.cpu().numpy().tobytes())
+        self._h = C.c_void_p()
+        with torch.cuda.device(device):
+            _cabi.check(L.flmr_comm_create(C.c_char_p(raw), self.rank, self.world, int(device.index), C.byref(self._h)))
+
+    def search(self, corpus, Q: torch.Tensor, k: int, relu: bool = False) -> Tuple[torch.Tensor, torch.Tensor]:
+        """``flmr_maxsim_topk_sharded``: (scores [B, k], global pids [B, k]) of the MERGED ranking, on every rank."""
+        import ctypes as C
+        from . import _cabi
+        from .maxsim import _prep_queries
+        Qd = _prep_queries(corpus, Q)
+        B, nq = Qd.size(0), Qd.size(1)
+        s = torch.empty((B, k), dtype=torch.float32, device=self.device)
+        p = torch.empty((B, k), dtype=torch.int64, device=self.device)
+        with torch.cuda.device(self.device):
+            _cabi.check(_cabi.lib().flmr_maxsim_topk_sharded(
+                corpus.handle, corpus.workspace(), self._h, C.c_void_p(Qd.data_ptr()), B, nq, k,
+                _cabi.FLAG_RELU if relu else 0, C.c_void_p(s.data_ptr()), C.c_void_p(p.data_ptr()),
+                C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)))
+        return s, p
+
+    def exchange(self, s: torch.Tensor, p: torch.Tensor, k: int) -> Tuple[torch.Tensor, torch.Tensor]:
+        """``flmr_topk_exchange`` for lists the caller already has (``[B, k_in]``, pid < 0 = empty entry)."""
+        import ctypes as C
+        from . import _cabi
+        s = s.to(self.device, torch.float32).contiguous()
+        p = p.to(self.device, torch.int64).contiguous()
+        B, k_in = s.shape
+        out_s = torch.empty((B, k), dtype=torch.float32, device=self.device)
+        out_p = torch.empty((B, k), dtype=torch.int64, device=self.device)
+        with torch.cuda.device(self.device):
+            _cabi.check(_cabi.lib().flmr_topk_exchange(
+                self._h, C.c_void_p(s.data_ptr()), C.c_void_p(p.data_ptr()), B, k_in, k,
+                C.c_void_p(out_s.data_ptr()), C.c_void_p(out_p.data_ptr()),
+                C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)))
+        return out_s, out_p
+
+    def close(self):
+        from . import _cabi
+        if self._h is not None:
+            torch.cuda.synchronize(self.device)
+            _cabi.lib().flmr_comm_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class ShardedSearcher:
     """``local_topk(Q, k) -> (scores [B,k], pids [B,k])`` runs on this rank's shard (global pids);
     ``merge(scores [R,B,k], pids [R,B,k], k) -> (scores [B,k], pids [B,k])`` merges the gathered

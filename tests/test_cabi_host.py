@@ -193,3 +193,20 @@ def test_pass_plan_random_shapes():
             if flags & 4:
                 final[q_first:q_first + n_q] += 1
         assert (covered == 1).all() and (final == 1).all(), (n_queries, nq)
+
+
+def test_comm_entry_points_validate_arguments():
+    """The C-level sharded search (flmr_comm_* / flmr_topk_exchange / flmr_maxsim_topk_sharded): argument checks
+    need neither a GPU nor NCCL."""
+    import ctypes as C
+    L = _cabi.lib()
+    h = C.c_void_p()
+    assert L.flmr_comm_create(None, 0, 1, 0, C.byref(h)) == 1 and b"null" in L.flmr_last_error()
+    buf = (C.c_char * 128)()
+    assert L.flmr_comm_create(buf, 2, 2, 0, C.byref(h)) == 1 and b"rank" in L.flmr_last_error()
+    assert L.flmr_comm_adopt(None, 0, C.byref(h)) == 1
+    assert L.flmr_comm_destroy(None) == 0
+    assert L.flmr_comm_info(None, None, None) == 1
+    assert L.flmr_topk_exchange(None, None, None, 1, 5, 5, None, None, None) == 1
+    assert L.flmr_maxsim_topk_sharded(None, None, None, None, 1, 32, 5, 0, None, None, None) == 1
+    assert L.flmr_comm_unique_id(None) == 1

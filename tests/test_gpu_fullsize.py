@@ -79,7 +79,41 @@ def _nccl_worker(rank, world, port, ret):
     corpus = R.FlatCorpus(torch.from_numpy(D[off[p0]:off[p1]]).to(torch.bfloat16), dl[p0:p1], device=rank, pid_base=p0)
     s, p = R.ShardedSearcher.from_corpus(corpus).search(torch.from_numpy(Q).cuda(rank), 10)
     rs, rp = O.topk(O.maxsim_scores(Q, D, dl), 10)
-    ret[rank] = bool(np.array_equal(p.cpu().numpy(), rp) and np.allclose(s.cpu().numpy(), rs, rtol=2e-5))
+    ok = bool(np.array_equal(p.cpu().numpy(), rp) and np.allclose(s.cpu().numpy(), rs, rtol=2e-5))
+    # the same through the C-level exchange (flmr_comm_create / flmr_maxsim_topk_sharded: the library's own NCCL
+    # communicator, one grouped all-gather + merge enqueued by one C call)
+    from ravqa_b200.sharded import NcclExchange
+    ex = NcclExchange(torch.device("cuda", rank))
+    s2, p2 = ex.search(corpus, torch.from_numpy(Q).cuda(rank), 10)
+    ok = ok and torch.equal(p2, p) and torch.equal(s2, s)
+    s3, p3 = ex.exchange(*R.maxsim_topk(corpus, torch.from_numpy(Q).cuda(rank), 10), 10)
+    ok = ok and torch.equal(p3, p) and torch.equal(s3, s)
+    # the reference-facing Searcher in sharded mode, from a flat index and from the reference-built PLAID directory
+    import tempfile
+    from helpers import GOLDEN_DIR
+    root = os.environ["FLMR_TEST_SHARED_TMP"]
+    if rank == 0:
+        R.save_flat_index(os.path.join(root, "e", "indexes", "flat"), torch.from_numpy(D), dl)
+    dist.barrier()
+    with R.Run().context(R.RunConfig(root=root, experiment="e")):
+        sr = R.Searcher(index="flat", config=R.ColBERTConfig(total_visible_gpus=1), shard_across_ranks=True)
+    rk = sr._search_all_Q(list(range(4)), torch.from_numpy(Q), k=10).todict()
+    ok = ok and all([pid for pid, _, _ in rk[b]] == rp[b].tolist() for b in range(4))
+    # k larger than the whole corpus and a filter: every rank returns the same short, merged lists
+    keep_fn = lambda pids: pids[(pids % 7 == 0)]                             # noqa: E731
+    rk = sr._search_all_Q(list(range(4)), torch.from_numpy(Q), k=5, filter_fn=keep_fn).todict()
+    full = O.maxsim_scores(Q, D, dl)
+    for b in range(4):
+        cand = np.arange(0, len(dl), 7)
+        want = cand[np.lexsort((cand, -full[b, cand].astype(np.float64)))[:5]]
+        ok = ok and [pid for pid, _, _ in rk[b]] == want.tolist()
+    z = np.load(os.path.join(GOLDEN_DIR, "callsites.npz"))
+    with R.Run().context(R.RunConfig(root=os.path.join(GOLDEN_DIR, "callsites", "ckpt"), experiment="temp_index_0")):
+        sp = R.Searcher(index="temp_index.nbits=8", config=R.ColBERTConfig(), shard_across_ranks=True)
+    rk = sp._search_all_Q(list(range(z["queries"].shape[0])), torch.from_numpy(z["queries"]), k=200).todict()
+    want = np.argsort(-z["exact_scores_bf16"], axis=1, kind="stable")
+    ok = ok and all([pid for pid, _, _ in rk[b]] == want[b].tolist() for b in range(want.shape[0]))   # k > n: all 160
+    ret[rank] = ok
     dist.barrier()
     dist.destroy_process_group()
 
@@ -89,6 +123,9 @@ def test_sharded_search_nccl():
     world = min(torch.cuda.device_count(), 4)
     if world < 2:
         pytest.skip("needs >= 2 GPUs")
+    import tempfile
     ret = mp.Manager().dict()
-    mp.spawn(_nccl_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
+    with tempfile.TemporaryDirectory() as tmp:
+        os.environ["FLMR_TEST_SHARED_TMP"] = tmp
+        mp.spawn(_nccl_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
     assert dict(ret) == {r: True for r in range(world)}
