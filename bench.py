@@ -428,6 +428,7 @@ def run_ours(args):
         # JSON line
         if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
             os.environ["NCCL_DEBUG"] = "WARN"
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # whatever NCCL still says goes to stderr
         dist.init_process_group("nccl", device_id=dev)
 
     # ---- this rank's shard of the synthetic corpus, generated on-device ----

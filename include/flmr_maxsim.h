@@ -75,6 +75,7 @@ extern "C" {
 typedef struct flmr_corpus flmr_corpus_t;       /* resident passage-token shard            */
 typedef struct flmr_workspace flmr_workspace_t; /* per-caller scratch (candidates, Q pad)  */
 typedef struct flmr_comm flmr_comm_t;           /* this rank's end of the shard exchange   */
+typedef struct flmr_corpus_builder flmr_corpus_builder_t; /* streaming index load          */
 
 typedef struct flmr_corpus_info {
   int64_t n_passages;     /* passages in this shard                                           */
@@ -108,6 +109,24 @@ int flmr_corpus_create(const void* tokens, const int32_t* h_doclens, int64_t n_p
                        int device, int64_t pid_base, unsigned flags, flmr_corpus_t** out);
 int flmr_corpus_destroy(flmr_corpus_t* corpus);
 int flmr_corpus_info(const flmr_corpus_t* corpus, flmr_corpus_info_t* out);
+
+/*
+ * Streaming construction of a corpus shard — the index LOAD path (replaces IndexLoader / ResidualEmbeddings.load_chunks,
+ * CB/search/index_loader.py:24-62, CB/indexing/codecs/residual_embeddings.py:24-69): the padded token matrix is
+ * allocated once from the doclens, then packed bf16 rows arrive IN ORDER, in chunks of any size, from host memory
+ * or straight from a file, through two pinned staging buffers (the host fill of one overlaps the DMA of the
+ * other; the file variant preads into pinned memory with 4 threads — no intermediate host copy).  If every
+ * doclen is a multiple of FLMR_TOKEN_GROUP the rows are copied straight into place, else a scatter kernel puts
+ * them into the padded layout.  finish() synchronises, builds the partition metadata and hands over the corpus
+ * (the builder is destroyed); *host_fill_seconds (may be NULL) = host time spent reading / copying into the
+ * staging buffers.  destroy() abandons a build.
+ */
+int flmr_corpus_builder_create(const int32_t* h_doclens, int64_t n_passages, int dim, int device,
+                               int64_t pid_base, flmr_corpus_builder_t** out);
+int flmr_corpus_builder_append(flmr_corpus_builder_t* b, const void* h_tokens_bf16, int64_t n_rows);
+int flmr_corpus_builder_append_file(flmr_corpus_builder_t* b, const char* path, int64_t byte_offset, int64_t n_rows);
+int flmr_corpus_builder_finish(flmr_corpus_builder_t* b, flmr_corpus_t** out, double* host_fill_seconds);
+int flmr_corpus_builder_destroy(flmr_corpus_builder_t* b);
 
 /* Scratch for searches on `corpus`.  max_queries (>= 1) sizes the per-CTA candidate buffer: a call with more
  * queries is processed in chunks of max_queries (each chunk: its scan passes + ONE merge launch).  max_nq

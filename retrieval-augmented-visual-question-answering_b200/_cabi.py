@@ -38,6 +38,8 @@ SYMBOLS = [
     "flmr_maxsim_scores", "flmr_maxsim_topk", "flmr_topk_merge", "flmr_topk_select", "flmr_plaid_decode",
     "flmr_maxsim_argmax", "flmr_maxsim_backward", "flmr_corpus_gather",
     "flmr_maxsim_argmax_grouped", "flmr_maxsim_backward_grouped",
+    "flmr_corpus_builder_create", "flmr_corpus_builder_append", "flmr_corpus_builder_append_file",
+    "flmr_corpus_builder_finish", "flmr_corpus_builder_destroy",
     "flmr_comm_unique_id", "flmr_comm_create", "flmr_comm_adopt", "flmr_comm_destroy", "flmr_comm_info",
     "flmr_topk_exchange", "flmr_maxsim_topk_sharded",
     "flmr_debug_maxsim_scores_simt", "flmr_debug_build_partition", "flmr_debug_plan_passes",
@@ -91,6 +93,11 @@ def lib() -> C.CDLL:
     L.flmr_maxsim_backward.argtypes = [vp, i32, i32, vp, i32, i32, vp, vp, vp, vp, i32, vp]
     L.flmr_maxsim_argmax_grouped.argtypes = [vp, i32, i32, vp, vp, i32, i32, vp, vp, i32, vp]
     L.flmr_maxsim_backward_grouped.argtypes = [vp, i32, i32, vp, i32, i32, vp, vp, vp, vp, i32, vp]
+    L.flmr_corpus_builder_create.argtypes = [vp, i64, i32, i32, i64, C.POINTER(vp)]
+    L.flmr_corpus_builder_append.argtypes = [vp, vp, i64]
+    L.flmr_corpus_builder_append_file.argtypes = [vp, C.c_char_p, i64, i64]
+    L.flmr_corpus_builder_finish.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_double)]
+    L.flmr_corpus_builder_destroy.argtypes = [vp]
     L.flmr_comm_unique_id.argtypes = [vp]
     L.flmr_comm_create.argtypes = [vp, i32, i32, i32, C.POINTER(vp)]
     L.flmr_comm_adopt.argtypes = [vp, i32, C.POINTER(vp)]

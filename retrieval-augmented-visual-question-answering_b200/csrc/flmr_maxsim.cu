@@ -10,6 +10,8 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <dlfcn.h>
+#include <fcntl.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <cmath>
@@ -20,7 +22,10 @@
 #include <limits>
 #include <mutex>
 #include <new>
+#include <cerrno>
+#include <ctime>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/flmr_maxsim.h"
@@ -109,20 +114,28 @@ int encode_rows_map(CUtensorMap* map, const void* base, uint64_t rows, uint32_t 
 
 // ---- helper kernels --------------------------------------------------------------------------------
 
-// Stage the resident queries of one pass: each query padded with zero rows to rbq*32 rows, the whole
-// block padded with zero rows to n_mtiles*128 rows.  One thread per 16 bytes.
+// Stage the resident queries of EVERY pass of a call in one launch (blockIdx.y = pass): each query padded
+// with zero rows to rbq*32 rows, the pass's block padded with zero rows to n_mtiles*128 rows, pass i at
+// qpad + i * kMtMax*128 rows.  One thread per 16 bytes.
+constexpr int kStageMaxPasses = 64;
+struct StagePass {
+  int32_t q_first, n_q, row0, rows, rbq, n_rows_pad;
+};
+struct StageParams {
+  StagePass pass[kStageMaxPasses];
+};
 __global__ void flmr_stage_queries_kernel(const uint4* __restrict__ q, uint4* __restrict__ qpad,
-                                          int nq_pass, int nq_total_rows, int row0, int rows_slice,
-                                          int rbq, int n_rows_pad) {
+                                          int nq_total_rows, const __grid_constant__ StageParams sp) {
+  const StagePass& ps = sp.pass[blockIdx.y];
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   const int r = idx >> 4, c = idx & 15;
-  if (r >= n_rows_pad) return;
-  const int rows_q = rbq * 32;
+  if (r >= ps.n_rows_pad) return;
+  const int rows_q = ps.rbq * 32;
   const int b = r / rows_q, i = r % rows_q;
   uint4 v = make_uint4(0u, 0u, 0u, 0u);
-  if (b < nq_pass && i < rows_slice)
-    v = q[(static_cast<int64_t>(b) * nq_total_rows + row0 + i) * 16 + c];
-  qpad[idx] = v;
+  if (b < ps.n_q && i < ps.rows)
+    v = q[(static_cast<int64_t>(ps.q_first + b) * nq_total_rows + ps.row0 + i) * 16 + c];
+  qpad[static_cast<int64_t>(blockIdx.y) * (kMtMax * kTileM * 16) + idx] = v;
 }
 
 // Copy passages into the padded layout: passage p occupies rows [poff[p], poff[p+1]) of dst, its
@@ -141,6 +154,28 @@ __global__ void flmr_repack_kernel(const uint4* __restrict__ src, const int64_t*
     const int64_t sj = j < len ? j : len - 1;
     dst[(d0 + j) * 16 + c] = src[(s0 - src_row_base + sj) * 16 + c];
   }
+}
+
+// Streamed corpus load: rows [s0, s0 + n) of the PACKED source order (staged at `src`) go to their place in the
+// padded layout; the last token of a passage is also copied over its padding rows.  Chunks need not start or end
+// on passage boundaries.  One half-warp per row; the passage of a row is found by binary search in `soff`.
+__global__ void flmr_scatter_rows_kernel(const uint4* __restrict__ src, const int64_t* __restrict__ soff,
+                                         const int64_t* __restrict__ poff, uint4* __restrict__ dst,
+                                         int64_t s0, int64_t n, int64_t n_passages) {
+  const int64_t r = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 4;
+  const int c = threadIdx.x & 15;
+  if (r >= n) return;
+  const int64_t srow = s0 + r;
+  int64_t lo = 0, hi = n_passages;          // largest p with soff[p] <= srow
+  while (hi - lo > 1) {
+    const int64_t mid = (lo + hi) >> 1;
+    if (soff[mid] <= srow) lo = mid; else hi = mid;
+  }
+  const uint4 v = src[r * 16 + c];
+  const int64_t d = poff[lo] + (srow - soff[lo]);
+  dst[d * 16 + c] = v;
+  if (srow == soff[lo + 1] - 1)             // last token: fill the group padding with copies
+    for (int64_t j = d + 1; j < poff[lo + 1]; ++j) dst[j * 16 + c] = v;
 }
 
 // Independent plain-SIMT MaxSim (test infrastructure): one block per (passage, query), one thread
@@ -484,11 +519,31 @@ struct flmr_corpus {
   CUtensorMap tmap_d;
 };
 
+// Streaming corpus construction (index load): the padded token matrix is allocated once, packed rows arrive in
+// order through two pinned staging buffers (host fill of one overlaps the DMA of the other).
+struct flmr_corpus_builder {
+  flmr_corpus* corpus = nullptr;        // under construction (owned until finish)
+  std::vector<int64_t> soff, poff;
+  std::vector<int32_t> doclens;
+  bool aligned = true;                  // every doclen a multiple of kGroup: rows land in place, no scatter
+  int64_t rows_done = 0;
+  int sm_count = 0;
+  cudaStream_t stream = nullptr;
+  static constexpr int kBufs = 2;
+  static constexpr int64_t kBufRows = (64ll << 20) / (kDim * 2);   // 64 MB of rows per staging buffer
+  void* h_pin[kBufs] = {nullptr, nullptr};
+  uint4* d_stage[kBufs] = {nullptr, nullptr};   // device staging (unaligned corpora only)
+  cudaEvent_t free_ev[kBufs] = {nullptr, nullptr};
+  int64_t *d_soff = nullptr, *d_poff = nullptr;
+  int next = 0;
+  double fill_s = 0.0;                  // host time spent filling the pinned buffers (read / memcpy)
+};
+
 struct flmr_workspace {
   const flmr_corpus* corpus = nullptr;
   int device = 0;
   int max_queries = 0, max_nq = 0;
-  __nv_bfloat16* d_qpad = nullptr;     // [kMtMax*128, 128] staged (zero-padded) queries of one pass
+  __nv_bfloat16* d_qpad = nullptr;     // [kStageMaxPasses][kMtMax*128, 128] staged (zero-padded) queries, one slot per pass
   uint64_t* d_cand_keys = nullptr;     // [n_ctas][max_queries][k] candidate keys of one call chunk
   float* d_acc = nullptr;              // [group][n_passages] lazily allocated (row-sliced queries)
   int64_t acc_capacity = 0;            // floats allocated at d_acc
@@ -702,15 +757,18 @@ int launch_scan(const flmr_corpus* c, flmr_workspace* ws, const ScanParams& p, c
   return FLMR_OK;
 }
 
-int stage_queries(flmr_workspace* ws, const void* d_q, int64_t q_first, int nq_pass, int nq,
-                  int row0, int rows_slice, int rbq, int n_mtiles, cudaStream_t st) {
-  const int n_rows_pad = n_mtiles * kTileM;
+// Stage passes [first, first + count) of `plan` into slots 0.. of the workspace's staging buffer.
+int stage_queries(flmr_workspace* ws, const void* d_q, int nq, const std::vector<PassPlan>& plan, size_t first,
+                  size_t count, cudaStream_t st) {
+  StageParams sp{};
+  for (size_t i = 0; i < count; ++i) {
+    const PassPlan& pp = plan[first + i];
+    sp.pass[i] = {pp.q_first, pp.n_q, pp.row0, pp.rows, pp.rbq, pp.n_mtiles * kTileM};
+  }
   const int threads = 256;
-  const int total = n_rows_pad * 16;
-  const uint4* src = reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(d_q) +
-                                                    q_first * nq * kDim);
-  flmr_stage_queries_kernel<<<(total + threads - 1) / threads, threads, 0, st>>>(
-      src, reinterpret_cast<uint4*>(ws->d_qpad), nq_pass, nq, row0, rows_slice, rbq, n_rows_pad);
+  dim3 grid((kMtMax * kTileM * 16 + threads - 1) / threads, static_cast<unsigned>(count));
+  flmr_stage_queries_kernel<<<grid, threads, 0, st>>>(reinterpret_cast<const uint4*>(d_q),
+                                                      reinterpret_cast<uint4*>(ws->d_qpad), nq, sp);
   FLMR_CUDA(cudaGetLastError());
   ++g_launches;
   return FLMR_OK;
@@ -805,13 +863,18 @@ int run_search(const flmr_corpus* c, flmr_workspace* ws, const void* d_q, int n_
     if (!d_all_c && nq > kRbMax * 32 && (rc = ensure_acc(ws, static_cast<int64_t>(group) * c->n_passages)))
       return rc;
     p.cand_q_stride = nqc;
-    for (const PassPlan& pp : plan) {
+    for (size_t pi = 0; pi < plan.size(); ++pi) {
+      const PassPlan& pp = plan[pi];
       // partial / final scores of query (group_first + acc_slot + i) live in row i of `acc`
       float* acc = d_all_c
                        ? d_all_c + static_cast<int64_t>(pp.group_first + pp.acc_slot) * c->n_passages
                        : (ws->d_acc ? ws->d_acc + static_cast<int64_t>(pp.acc_slot) * c->n_passages : nullptr);
-      if ((rc = stage_queries(ws, d_qc, pp.q_first, pp.n_q, nq, pp.row0, pp.rows, pp.rbq, pp.n_mtiles, st)))
+      // the queries of up to kStageMaxPasses passes are staged by ONE launch, ahead of their scans
+      if (pi % kStageMaxPasses == 0 &&
+          (rc = stage_queries(ws, d_qc, nq, plan, pi, std::min<size_t>(kStageMaxPasses, plan.size() - pi), st)))
         return rc;
+      p.q_pad = reinterpret_cast<const uint4*>(ws->d_qpad) +
+                static_cast<int64_t>(pi % kStageMaxPasses) * (kMtMax * kTileM * 16);
       p.n_mtiles = pp.n_mtiles;
       p.nq_pass = pp.n_q;
       p.rbq = pp.rbq;
@@ -824,6 +887,59 @@ int run_search(const flmr_corpus* c, flmr_workspace* ws, const void* d_q, int n_
     if (k > 0 && (rc = launch_merge_keys(c, ws, nqc, k, d_topk_scores + static_cast<int64_t>(c0) * k,
                                          d_topk_pids + static_cast<int64_t>(c0) * k, st)))
       return rc;
+  }
+  return FLMR_OK;
+}
+
+// Everything a corpus needs besides its token matrix: offsets / lengths, the CTA partition + per-tile metadata,
+// the TMA descriptor, the kernel's shared-memory attribute.  Shared by flmr_corpus_create and the streaming builder.
+int finish_corpus(flmr_corpus* c, const std::vector<int64_t>& poff, const int32_t* h_doclens, int sm_count) {
+  const int64_t n_passages = c->n_passages;
+  const int64_t n_rows = c->n_rows;
+  int rc = FLMR_OK;
+  auto bail = [](int code) { return code; };
+  struct {
+    int multiProcessorCount;
+  } prop{sm_count};
+  // --- offsets / lengths (SIMT cross-check kernel, info) ---
+  {
+    std::vector<int32_t> lens(h_doclens, h_doclens + n_passages);
+    if ((rc = dev_upload(&c->d_poff, poff, &c->hbm_bytes))) return bail(rc);
+    if ((rc = dev_upload(&c->d_doclen, lens, &c->hbm_bytes))) return bail(rc);
+  }
+
+  // --- partition + tile metadata ---
+  int n_ctas = prop.multiProcessorCount;
+#ifdef FLMR_DEBUG
+  if (const char* e = getenv("FLMR_NUM_CTAS")) n_ctas = std::max(1, atoi(e));
+#endif
+  n_ctas = static_cast<int>(std::min<int64_t>(n_ctas, n_passages));
+  c->n_ctas = n_ctas;
+  {
+    std::vector<int32_t> row_begin, first_pid;
+    std::vector<int64_t> tile_base;
+    std::vector<uint32_t> end_mask;
+    build_partition(poff, n_ctas, kTileN, &row_begin, &tile_base, &end_mask, &first_pid);
+    c->n_tiles = static_cast<int64_t>(end_mask.size());
+    if ((rc = dev_upload(&c->d_cta_row_begin, row_begin, &c->hbm_bytes))) return bail(rc);
+    if ((rc = dev_upload(&c->d_cta_tile_base, tile_base, &c->hbm_bytes))) return bail(rc);
+    if ((rc = dev_upload(&c->d_tile_end_mask, end_mask, &c->hbm_bytes))) return bail(rc);
+    if ((rc = dev_upload(&c->d_tile_first_pid, first_pid, &c->hbm_bytes))) return bail(rc);
+  }
+  if ((rc = encode_rows_map(&c->tmap_d, c->d_tokens, static_cast<uint64_t>(n_rows), kTileN)))
+    return bail(rc);
+  {  // per-device function attribute, set here (idempotent) rather than at launch time
+    cudaError_t e1 = cudaFuncSetAttribute(flmr_scan_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          ScanSmem::kBytes);
+#ifdef FLMR_DEBUG
+    cudaError_t e2 = cudaFuncSetAttribute(flmr_scan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          ScanSmem::kBytes);
+#else
+    cudaError_t e2 = cudaSuccess;
+#endif
+    if (e1 != cudaSuccess || e2 != cudaSuccess)
+      return bail(fail(FLMR_ERR_CUDA, "cannot raise the dynamic shared memory limit to %d bytes: %s",
+                       ScanSmem::kBytes, cudaGetErrorString(e1 != cudaSuccess ? e1 : e2)));
   }
   return FLMR_OK;
 }
@@ -956,46 +1072,7 @@ int flmr_corpus_create(const void* tokens, const int32_t* h_doclens, int64_t n_p
       return bail(fail(FLMR_ERR_CUDA, "corpus repack failed: %s", cudaGetErrorString(e)));
   }
 
-  // --- offsets / lengths (SIMT cross-check kernel, info) ---
-  {
-    std::vector<int32_t> lens(h_doclens, h_doclens + n_passages);
-    if ((rc = dev_upload(&c->d_poff, poff, &c->hbm_bytes))) return bail(rc);
-    if ((rc = dev_upload(&c->d_doclen, lens, &c->hbm_bytes))) return bail(rc);
-  }
-
-  // --- partition + tile metadata ---
-  int n_ctas = prop.multiProcessorCount;
-#ifdef FLMR_DEBUG
-  if (const char* e = getenv("FLMR_NUM_CTAS")) n_ctas = std::max(1, atoi(e));
-#endif
-  n_ctas = static_cast<int>(std::min<int64_t>(n_ctas, n_passages));
-  c->n_ctas = n_ctas;
-  {
-    std::vector<int32_t> row_begin, first_pid;
-    std::vector<int64_t> tile_base;
-    std::vector<uint32_t> end_mask;
-    build_partition(poff, n_ctas, kTileN, &row_begin, &tile_base, &end_mask, &first_pid);
-    c->n_tiles = static_cast<int64_t>(end_mask.size());
-    if ((rc = dev_upload(&c->d_cta_row_begin, row_begin, &c->hbm_bytes))) return bail(rc);
-    if ((rc = dev_upload(&c->d_cta_tile_base, tile_base, &c->hbm_bytes))) return bail(rc);
-    if ((rc = dev_upload(&c->d_tile_end_mask, end_mask, &c->hbm_bytes))) return bail(rc);
-    if ((rc = dev_upload(&c->d_tile_first_pid, first_pid, &c->hbm_bytes))) return bail(rc);
-  }
-  if ((rc = encode_rows_map(&c->tmap_d, c->d_tokens, static_cast<uint64_t>(n_rows), kTileN)))
-    return bail(rc);
-  {  // per-device function attribute, set here (idempotent) rather than at launch time
-    cudaError_t e1 = cudaFuncSetAttribute(flmr_scan_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          ScanSmem::kBytes);
-#ifdef FLMR_DEBUG
-    cudaError_t e2 = cudaFuncSetAttribute(flmr_scan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          ScanSmem::kBytes);
-#else
-    cudaError_t e2 = cudaSuccess;
-#endif
-    if (e1 != cudaSuccess || e2 != cudaSuccess)
-      return bail(fail(FLMR_ERR_CUDA, "cannot raise the dynamic shared memory limit to %d bytes: %s",
-                       ScanSmem::kBytes, cudaGetErrorString(e1 != cudaSuccess ? e1 : e2)));
-  }
+  if ((rc = finish_corpus(c, poff, h_doclens, prop.multiProcessorCount))) return bail(rc);
   *out = c;
   return FLMR_OK;
 }
@@ -1011,6 +1088,193 @@ int flmr_corpus_destroy(flmr_corpus_t* c) {
   cudaFree(c->d_tile_end_mask);
   cudaFree(c->d_tile_first_pid);
   delete c;
+  return FLMR_OK;
+}
+
+int flmr_corpus_builder_create(const int32_t* h_doclens, int64_t n_passages, int dim, int device,
+                               int64_t pid_base, flmr_corpus_builder_t** out) {
+  if (!out) return fail(FLMR_ERR_INVALID_ARG, "out is null");
+  *out = nullptr;
+  if (dim != kDim) return fail(FLMR_ERR_UNSUPPORTED, "dim=%d (only %d is supported)", dim, kDim);
+  if (n_passages <= 0 || !h_doclens) return fail(FLMR_ERR_INVALID_ARG, "empty corpus or null doclens");
+  flmr_corpus_builder* b = new (std::nothrow) flmr_corpus_builder();
+  if (!b) return fail(FLMR_ERR_OOM, "host allocation failed");
+  auto bail = [&](int code) {
+    flmr_corpus_builder_destroy(b);
+    return code;
+  };
+  b->soff.resize(n_passages + 1);
+  b->poff.resize(n_passages + 1);
+  b->doclens.assign(h_doclens, h_doclens + n_passages);
+  b->soff[0] = b->poff[0] = 0;
+  for (int64_t p = 0; p < n_passages; ++p) {
+    const int32_t len = h_doclens[p];
+    if (len < 1)
+      return bail(fail(FLMR_ERR_INVALID_ARG, "passage %lld has length %d; zero-length passages have no defined MaxSim score",
+                       (long long)p, len));
+    b->soff[p + 1] = b->soff[p] + len;
+    b->poff[p + 1] = b->poff[p] + (len + kGroup - 1) / kGroup * kGroup;
+    b->aligned &= (len % kGroup == 0);
+  }
+  const int64_t n_rows = b->poff[n_passages];
+  if (n_rows + kTileN >= (1ll << 31))
+    return bail(fail(FLMR_ERR_UNSUPPORTED, "%lld stored token rows exceed the 2^31 per-shard limit; shard the corpus",
+                     (long long)n_rows));
+  DeviceGuard guard(device);
+  if (!guard.ok) return bail(fail(FLMR_ERR_CUDA, "cudaSetDevice(%d) failed", device));
+  cudaDeviceProp prop;
+  cudaError_t e = cudaGetDeviceProperties(&prop, device);
+  if (e != cudaSuccess) return bail(fail(FLMR_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e)));
+  if (prop.major != 10)
+    return bail(fail(FLMR_ERR_UNSUPPORTED, "device %d is sm_%d%d; this library is sm_100a only", device, prop.major,
+                     prop.minor));
+  b->sm_count = prop.multiProcessorCount;
+  flmr_corpus* c = new (std::nothrow) flmr_corpus();
+  if (!c) return bail(fail(FLMR_ERR_OOM, "host allocation failed"));
+  b->corpus = c;
+  c->device = device;
+  c->n_passages = n_passages;
+  c->n_tokens = b->soff[n_passages];
+  c->n_rows = n_rows;
+  c->pid_base = pid_base;
+  const size_t bytes = static_cast<size_t>(n_rows) * kDim * 2;
+  if ((e = cudaMalloc(reinterpret_cast<void**>(&c->d_tokens), bytes)) != cudaSuccess)
+    return bail(fail(FLMR_ERR_OOM, "cudaMalloc(%zu B) for the token matrix failed: %s", bytes, cudaGetErrorString(e)));
+  c->hbm_bytes += static_cast<int64_t>(bytes);
+  const size_t buf_bytes = static_cast<size_t>(flmr_corpus_builder::kBufRows) * kDim * 2;
+  if ((e = cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking)) != cudaSuccess)
+    return bail(fail(FLMR_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)));
+  for (int i = 0; i < flmr_corpus_builder::kBufs; ++i) {
+    if ((e = cudaHostAlloc(&b->h_pin[i], buf_bytes, cudaHostAllocDefault)) != cudaSuccess ||
+        (e = cudaEventCreateWithFlags(&b->free_ev[i], cudaEventDisableTiming)) != cudaSuccess ||
+        (!b->aligned && (e = cudaMalloc(reinterpret_cast<void**>(&b->d_stage[i]), buf_bytes)) != cudaSuccess))
+      return bail(fail(FLMR_ERR_OOM, "staging buffers: %s", cudaGetErrorString(e)));
+  }
+  if (!b->aligned) {
+    int rc;
+    if ((rc = dev_upload(&b->d_soff, b->soff, nullptr)) || (rc = dev_upload(&b->d_poff, b->poff, nullptr)))
+      return bail(rc);
+  }
+  *out = b;
+  return FLMR_OK;
+}
+
+extern "C++" {
+namespace {
+// Feed `n_rows` packed rows through the staging ring; `fill(dst, row0, rows)` writes rows [row0, row0 + rows) of
+// this append into pinned memory (memcpy from a host buffer, or pread from a file).
+template <typename Fill>
+int builder_feed(flmr_corpus_builder* b, int64_t n_rows, Fill fill) {
+  flmr_corpus* c = b->corpus;
+  if (n_rows < 0 || b->rows_done + n_rows > c->n_tokens)
+    return fail(FLMR_ERR_INVALID_ARG, "append of %lld rows overruns the %lld rows the doclens announce (%lld done)",
+                (long long)n_rows, (long long)c->n_tokens, (long long)b->rows_done);
+  DeviceGuard guard(c->device);
+  if (!guard.ok) return fail(FLMR_ERR_CUDA, "cudaSetDevice(%d) failed", c->device);
+  for (int64_t r0 = 0; r0 < n_rows; r0 += flmr_corpus_builder::kBufRows) {
+    const int64_t rows = std::min<int64_t>(flmr_corpus_builder::kBufRows, n_rows - r0);
+    const int i = b->next;
+    b->next = (b->next + 1) % flmr_corpus_builder::kBufs;
+    FLMR_CUDA(cudaEventSynchronize(b->free_ev[i]));          // the DMA that last read this buffer is done
+    timespec t0, t1;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    if (int rc = fill(b->h_pin[i], r0, rows)) return rc;
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    b->fill_s += (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
+    const size_t bytes = static_cast<size_t>(rows) * kDim * 2;
+    const int64_t s0 = b->rows_done;
+    if (b->aligned) {                                        // packed order == stored order: straight into place
+      FLMR_CUDA(cudaMemcpyAsync(c->d_tokens + s0 * kDim, b->h_pin[i], bytes, cudaMemcpyHostToDevice, b->stream));
+    } else {
+      FLMR_CUDA(cudaMemcpyAsync(b->d_stage[i], b->h_pin[i], bytes, cudaMemcpyHostToDevice, b->stream));
+      const int threads = 256;
+      flmr_scatter_rows_kernel<<<static_cast<unsigned>((rows * 16 + threads - 1) / threads), threads, 0, b->stream>>>(
+          b->d_stage[i], b->d_soff, b->d_poff, reinterpret_cast<uint4*>(c->d_tokens), s0, rows, c->n_passages);
+      FLMR_CUDA(cudaGetLastError());
+      ++g_launches;
+    }
+    FLMR_CUDA(cudaEventRecord(b->free_ev[i], b->stream));
+    b->rows_done += rows;
+  }
+  return FLMR_OK;
+}
+}  // namespace
+}  // extern "C++"
+
+int flmr_corpus_builder_append(flmr_corpus_builder_t* b, const void* h_tokens_bf16, int64_t n_rows) {
+  if (!b || !h_tokens_bf16) return fail(FLMR_ERR_INVALID_ARG, "null argument");
+  const char* src = static_cast<const char*>(h_tokens_bf16);
+  return builder_feed(b, n_rows, [&](void* dst, int64_t r0, int64_t rows) {
+    memcpy(dst, src + r0 * kDim * 2, static_cast<size_t>(rows) * kDim * 2);
+    return FLMR_OK;
+  });
+}
+
+int flmr_corpus_builder_append_file(flmr_corpus_builder_t* b, const char* path, int64_t byte_offset, int64_t n_rows) {
+  if (!b || !path) return fail(FLMR_ERR_INVALID_ARG, "null argument");
+  const int fd = open(path, O_RDONLY);
+  if (fd < 0) return fail(FLMR_ERR_INVALID_ARG, "cannot open %s: %s", path, strerror(errno));
+  // the file is read straight into pinned memory by a few threads (pread is thread-safe): no intermediate copy
+  const int rc = builder_feed(b, n_rows, [&](void* dst, int64_t r0, int64_t rows) {
+    constexpr int kThreads = 4;
+    const int64_t total = rows * kDim * 2, per = (total + kThreads - 1) / kThreads;
+    int errs[kThreads] = {0, 0, 0, 0};
+    std::thread th[kThreads];
+    for (int t = 0; t < kThreads; ++t)
+      th[t] = std::thread([&, t]() {
+        int64_t a = t * per, e = std::min<int64_t>(total, a + per);
+        while (a < e) {
+          const ssize_t got = pread(fd, static_cast<char*>(dst) + a, static_cast<size_t>(e - a),
+                                    byte_offset + r0 * kDim * 2 + a);
+          if (got <= 0) {
+            errs[t] = got == 0 ? -1 : errno;
+            return;
+          }
+          a += got;
+        }
+      });
+    for (auto& x : th) x.join();
+    for (int e : errs)
+      if (e) return fail(FLMR_ERR_INVALID_ARG, "short read from %s (%s)", path, e < 0 ? "end of file" : strerror(e));
+    return static_cast<int>(FLMR_OK);
+  });
+  close(fd);
+  return rc;
+}
+
+int flmr_corpus_builder_finish(flmr_corpus_builder_t* b, flmr_corpus_t** out, double* host_fill_seconds) {
+  if (!b || !out) return fail(FLMR_ERR_INVALID_ARG, "null argument");
+  *out = nullptr;
+  flmr_corpus* c = b->corpus;
+  if (b->rows_done != c->n_tokens)
+    return fail(FLMR_ERR_INVALID_ARG, "%lld rows appended, the doclens announce %lld", (long long)b->rows_done,
+                (long long)c->n_tokens);
+  DeviceGuard guard(c->device);
+  if (!guard.ok) return fail(FLMR_ERR_CUDA, "cudaSetDevice(%d) failed", c->device);
+  FLMR_CUDA(cudaStreamSynchronize(b->stream));
+  if (int rc = finish_corpus(c, b->poff, b->doclens.data(), b->sm_count)) return rc;
+  if (host_fill_seconds) *host_fill_seconds = b->fill_s;
+  b->corpus = nullptr;     // ownership passes to the caller
+  flmr_corpus_builder_destroy(b);
+  *out = c;
+  return FLMR_OK;
+}
+
+int flmr_corpus_builder_destroy(flmr_corpus_builder_t* b) {
+  if (!b) return FLMR_OK;
+  const int device = b->corpus ? b->corpus->device : -1;
+  if (b->stream) cudaStreamSynchronize(b->stream);
+  for (int i = 0; i < flmr_corpus_builder::kBufs; ++i) {
+    if (b->h_pin[i]) cudaFreeHost(b->h_pin[i]);
+    if (b->d_stage[i]) cudaFree(b->d_stage[i]);
+    if (b->free_ev[i]) cudaEventDestroy(b->free_ev[i]);
+  }
+  cudaFree(b->d_soff);
+  cudaFree(b->d_poff);
+  if (b->stream) cudaStreamDestroy(b->stream);
+  if (b->corpus) flmr_corpus_destroy(b->corpus);
+  (void)device;
+  delete b;
   return FLMR_OK;
 }
 
@@ -1048,7 +1312,7 @@ int flmr_workspace_create(const flmr_corpus_t* c, int max_queries, int max_nq,
     return code;
   };
   cudaError_t e;
-  const size_t qbytes = static_cast<size_t>(kMtMax) * kTileM * kDim * 2;
+  const size_t qbytes = static_cast<size_t>(kStageMaxPasses) * kMtMax * kTileM * kDim * 2;   // 10 MB
   if ((e = cudaMalloc(reinterpret_cast<void**>(&ws->d_qpad), qbytes)) != cudaSuccess ||
       (e = cudaMemset(ws->d_qpad, 0, qbytes)) != cudaSuccess ||
       (e = cudaMalloc(reinterpret_cast<void**>(&ws->d_cand_keys),

@@ -86,6 +86,25 @@ def finalize_chunked_index(path: str, num_chunks: int) -> dict:
     return meta
 
 
+def index_token_files(path: str):
+    """(doclens of the whole index int32 [n_passages], [(token file, first passage, passages, rows), ...]) —
+    what a streaming loader needs to pick the byte ranges of a passage shard without reading any token."""
+    with open(os.path.join(path, "metadata.json")) as f:
+        meta = json.load(f)
+    if meta.get("format") != FORMAT:
+        raise ValueError("%s is not a %s index" % (path, FORMAT))
+    if meta.get("num_chunks", 0) == 0:
+        doclens = np.load(os.path.join(path, "doclens.npy")).astype(np.int32)
+        return doclens, [(os.path.join(path, "tokens.bf16"), 0, len(doclens), int(doclens.sum()))]
+    dls, files, offset = [], [], 0
+    for c in range(meta["num_chunks"]):
+        dl = np.load(os.path.join(path, "doclens.%d.npy" % c)).astype(np.int32)
+        files.append((os.path.join(path, "tokens.%d.bf16" % c), offset, len(dl), int(dl.sum())))
+        dls.append(dl)
+        offset += len(dl)
+    return np.concatenate(dls), files
+
+
 def _read_tokens(fname: str, n_rows: int, dim: int, row0: int = 0, row1: Optional[int] = None) -> torch.Tensor:
     row1 = n_rows if row1 is None else row1
     mm = np.memmap(fname, dtype=np.int16, mode="r", shape=(n_rows, dim))

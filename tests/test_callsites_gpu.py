@@ -290,3 +290,39 @@ def test_searcher_corner_cases(tmp_path):
     assert [(p, r) for p, r, _ in back.todict()[7]] == [(p, r) for p, r, _ in rk.todict()[7]]
     exact = O.topk(O.maxsim_scores(Q, D, dl), 3)[1]
     assert [p for p, _, _ in rk.todict()[9]] == exact[1].tolist()
+
+
+@pytest.mark.parametrize("aligned", [True, False])
+def test_streamed_index_load_equals_in_memory_corpus(tmp_path, aligned):
+    """FlatCorpus.from_index (C-level builder: pread -> pinned ring -> H2D -> padded layout; scatter kernel when
+    doclens are not multiples of 4) gives the same corpus as handing the tensors over — whole index and shards,
+    single-file and chunked layouts."""
+    import ravqa_b200 as R
+    from oracle import maxsim_oracle as O
+    from ravqa_b200.index_io import finalize_chunked_index, save_flat_chunk
+    Q, D, dl = O.synth(700, 40, 3, 64, seed=31, ragged=not aligned)
+    if aligned:
+        assert (dl % 4 == 0).all()
+    Dt = torch.from_numpy(D).to(torch.bfloat16)
+    ref = R.FlatCorpus(Dt, dl)
+    want = R.maxsim_scores(ref, torch.from_numpy(Q))
+    one = str(tmp_path / "one")
+    R.save_flat_index(one, Dt, dl)
+    chunked = str(tmp_path / "chunked")
+    off = np.concatenate([[0], np.cumsum(dl)])
+    for c, (a, b) in enumerate([(0, 250), (250, 251), (251, 700)]):
+        save_flat_chunk(chunked, c, a, Dt[off[a]:off[b]], dl[a:b])
+    finalize_chunked_index(chunked, 3)
+    for path in (one, chunked):
+        got = R.FlatCorpus.from_index(path)
+        assert got.load_stats["gigabytes"] > 0 and got.info.adopted == 0
+        assert torch.equal(R.maxsim_scores(got, torch.from_numpy(Q)), want)
+        parts = [R.FlatCorpus.from_index(path, rank=r, world_size=3) for r in range(3)]
+        assert sum(p.n_passages for p in parts) == 700 and parts[1].pid_base == parts[0].n_passages
+        cat = torch.cat([R.maxsim_scores(p, torch.from_numpy(Q)) for p in parts], dim=1)
+        assert torch.equal(cat, want)
+    # more ranks than passages: the surplus ranks get no corpus
+    tiny = str(tmp_path / "tiny")
+    R.save_flat_index(tiny, Dt[: off[2]], dl[:2])
+    shards = [R.FlatCorpus.from_index(tiny, rank=r, world_size=4) for r in range(4)]
+    assert sum(s.n_passages for s in shards if s is not None) == 2 and any(s is None for s in shards)
