@@ -115,7 +115,7 @@ int flmr_corpus_info(const flmr_corpus_t* corpus, flmr_corpus_info_t* out);
  * CB/search/index_loader.py:24-62, CB/indexing/codecs/residual_embeddings.py:24-69): the padded token matrix is
  * allocated once from the doclens, then packed bf16 rows arrive IN ORDER, in chunks of any size, from host memory
  * or straight from a file, through two pinned staging buffers (the host fill of one overlaps the DMA of the
- * other; the file variant preads into pinned memory with 4 threads — no intermediate host copy).  If every
+ * other; the file variant preads into pinned memory with 8 threads — no intermediate host copy).  If every
  * doclen is a multiple of FLMR_TOKEN_GROUP the rows are copied straight into place, else a scatter kernel puts
  * them into the padded layout.  finish() synchronises, builds the partition metadata and hands over the corpus
  * (the builder is destroyed); *host_fill_seconds (may be NULL) = host time spent reading / copying into the
@@ -245,6 +245,9 @@ int flmr_corpus_gather(const flmr_corpus_t* corpus, const int64_t* d_pids, int64
  *                       d_rowmax (optional, fp32, same shape) receives the maximum itself: summed over i it
  *                       is score[b, p], so for a training-sized batch this one launch is the forward AND
  *                       saves what the backward needs (4 B per pair instead of the Nd scores).
+ *                       Two kernels behind it: a warp-MMA one for small batches (a RAG re-score of 5 passages) and,
+ *                       from 16M (query row, token) pairs up, a tcgen05 one (documents compacted to their unmasked
+ *                       tokens, then a TMA / TMEM pipeline with the query tile stationary).
  * flmr_maxsim_backward: given d_grad[b, p] = dLoss/dScore[b, p],
  *                         d_dq[b, i, :]                  = sum_p grad[b, p] * D[p, argmax[b, p, i], :]
  *                         d_dd[p, argmax[b, p, i], :]   += grad[b, p] * Q[b, i, :]      (d_dd zeroed first)
@@ -261,6 +264,17 @@ int flmr_maxsim_argmax(const void* d_q, int n_queries, int nq, const void* d_doc
 int flmr_maxsim_backward(const void* d_q, int n_queries, int nq, const void* d_docs, int n_docs, int nd,
                          const int32_t* d_argmax, const float* d_grad, float* d_dq, float* d_dd,
                          int device, void* stream);
+
+/*
+ * The loss head of ColBERT.compute_ib_loss_new (CB/modeling/colbert.py:82-113) on top of flmr_maxsim_argmax's
+ * d_rowmax: scores[b, p] = sum_i rowmax[b, p, i]; cross-entropy of row b against the positive at column
+ * label0 + b * nway (colbert.py:103-111; label0 = rank * B * nway with cross-rank negatives); and its gradient,
+ * one launch instead of torch's sum + log_softmax + nll_loss and their backward kernels:
+ *   d_scores fp32 [n_queries, n_docs]     d_loss_per_query fp32 [n_queries] (the loss is their mean)
+ *   d_dscores fp32 [n_queries, n_docs] = d mean-loss / d scores — the d_grad operand of flmr_maxsim_backward
+ */
+int flmr_ib_loss(const float* d_rowmax, int n_queries, int n_docs, int nq, int nway, int label0,
+                 float* d_scores, float* d_loss_per_query, float* d_dscores, int device, void* stream);
 
 /*
  * Block-diagonal ("aligned") form of the two calls above: query b meets only ITS docs_per_query documents,
@@ -283,6 +297,11 @@ int flmr_maxsim_backward_grouped(const void* d_q, int n_queries, int nq, const v
  * flmr_maxsim_scores), independent of the tensor-core kernel. */
 int flmr_debug_maxsim_scores_simt(const flmr_corpus_t* corpus, const void* d_q, int n_queries,
                                   int nq, unsigned flags, float* d_out_scores, void* stream);
+
+/* Test infrastructure: which kernel flmr_maxsim_argmax(_grouped) runs on the calling thread — 0 = chosen by size
+ * (the product behaviour), 1 = the warp-MMA kernel, 2 = the tcgen05 kernel — so tests can hold either against
+ * the other and the oracle at any shape. */
+int flmr_debug_set_argmax_path(int path);
 
 /* Test infrastructure, host-only (no GPU needed): the token-balanced CTA partition + per-tile
  * passage-end metadata the scan kernel consumes, for `n_ctas` persistent CTAs and

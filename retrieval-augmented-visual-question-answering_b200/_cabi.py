@@ -37,12 +37,12 @@ SYMBOLS = [
     "flmr_workspace_create", "flmr_workspace_destroy", "flmr_workspace_status",
     "flmr_maxsim_scores", "flmr_maxsim_topk", "flmr_topk_merge", "flmr_topk_select", "flmr_plaid_decode",
     "flmr_maxsim_argmax", "flmr_maxsim_backward", "flmr_corpus_gather",
-    "flmr_maxsim_argmax_grouped", "flmr_maxsim_backward_grouped",
+    "flmr_maxsim_argmax_grouped", "flmr_maxsim_backward_grouped", "flmr_ib_loss",
     "flmr_corpus_builder_create", "flmr_corpus_builder_append", "flmr_corpus_builder_append_file",
     "flmr_corpus_builder_finish", "flmr_corpus_builder_destroy",
     "flmr_comm_unique_id", "flmr_comm_create", "flmr_comm_adopt", "flmr_comm_destroy", "flmr_comm_info",
     "flmr_topk_exchange", "flmr_maxsim_topk_sharded",
-    "flmr_debug_maxsim_scores_simt", "flmr_debug_build_partition", "flmr_debug_plan_passes",
+    "flmr_debug_maxsim_scores_simt", "flmr_debug_set_argmax_path", "flmr_debug_build_partition", "flmr_debug_plan_passes",
     "flmr_launch_count", "flmr_set_profiling", "flmr_scan_kernel_stats",
 ]
 
@@ -91,6 +91,7 @@ def lib() -> C.CDLL:
     L.flmr_corpus_gather.argtypes = [vp, vp, i64, i32, vp, vp, vp]
     L.flmr_maxsim_argmax.argtypes = [vp, i32, i32, vp, vp, i32, i32, vp, vp, i32, vp]
     L.flmr_maxsim_backward.argtypes = [vp, i32, i32, vp, i32, i32, vp, vp, vp, vp, i32, vp]
+    L.flmr_ib_loss.argtypes = [vp, i32, i32, i32, i32, i32, vp, vp, vp, i32, vp]
     L.flmr_maxsim_argmax_grouped.argtypes = [vp, i32, i32, vp, vp, i32, i32, vp, vp, i32, vp]
     L.flmr_maxsim_backward_grouped.argtypes = [vp, i32, i32, vp, i32, i32, vp, vp, vp, vp, i32, vp]
     L.flmr_corpus_builder_create.argtypes = [vp, i64, i32, i32, i64, C.POINTER(vp)]
@@ -106,6 +107,7 @@ def lib() -> C.CDLL:
     L.flmr_topk_exchange.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp, vp]
     L.flmr_maxsim_topk_sharded.argtypes = [vp, vp, vp, vp, i32, i32, i32, u32, vp, vp, vp]
     L.flmr_debug_maxsim_scores_simt.argtypes = [vp, vp, i32, i32, u32, vp, vp]
+    L.flmr_debug_set_argmax_path.argtypes = [i32]
     L.flmr_debug_build_partition.argtypes = [vp, i64, i32, vp, vp, vp, vp, i64, C.POINTER(i64)]
     L.flmr_debug_plan_passes.argtypes = [i32, i32, vp, i32, C.POINTER(i32)]
     L.flmr_launch_count.restype = i64

@@ -97,7 +97,7 @@ class FlatCorpus:
         token-balanced passage shard of it — into HBM.
 
         The token files are streamed by the C-level corpus builder: ``pread`` straight into two pinned staging
-        buffers (4 reader threads, the fill of one buffer overlaps the DMA of the other) and from there into the
+        buffers (8 reader threads, the fill of one buffer overlaps the DMA of the other) and from there into the
         padded layout — no numpy copy of the shard, no pageable ``cudaMemcpy``.  ``load_stats`` records seconds
         and GB/s (replaces IndexLoader / ResidualEmbeddings.load_chunks, colbert/search/index_loader.py:24-62)."""
         import time

@@ -31,6 +31,7 @@
 #include "../../include/flmr_maxsim.h"
 #include "flmr_scan_kernel.cuh"
 #include "flmr_train_kernels.cuh"
+#include "flmr_train_tc_kernel.cuh"
 
 namespace {
 
@@ -1216,9 +1217,9 @@ int flmr_corpus_builder_append_file(flmr_corpus_builder_t* b, const char* path, 
   if (fd < 0) return fail(FLMR_ERR_INVALID_ARG, "cannot open %s: %s", path, strerror(errno));
   // the file is read straight into pinned memory by a few threads (pread is thread-safe): no intermediate copy
   const int rc = builder_feed(b, n_rows, [&](void* dst, int64_t r0, int64_t rows) {
-    constexpr int kThreads = 4;
+    constexpr int kThreads = 8;
     const int64_t total = rows * kDim * 2, per = (total + kThreads - 1) / kThreads;
-    int errs[kThreads] = {0, 0, 0, 0};
+    int errs[kThreads] = {};
     std::thread th[kThreads];
     for (int t = 0; t < kThreads; ++t)
       th[t] = std::thread([&, t]() {
@@ -1460,6 +1461,69 @@ int flmr_corpus_gather(const flmr_corpus_t* c, const int64_t* d_pids, int64_t n_
   return FLMR_OK;
 }
 
+// ---- the tcgen05 route of the arg-max forward (flmr_train_tc_kernel.cuh) --------------------------------------
+thread_local int g_argmax_path = 0;   // 0 = by size, 1 = warp-MMA kernel, 2 = tcgen05 kernel (flmr_debug_set_argmax_path)
+
+static int argmax_tc(const void* d_q, int n_queries, int nq, const void* d_docs, const uint8_t* d_mask, int n_per,
+                     int stride_b, int nd, int32_t* d_argmax, float* d_rowmax, cudaStream_t st) {
+  const int64_t n_total = stride_b ? static_cast<int64_t>(n_queries) * n_per : n_per;
+  const int nd_c = (nd + kTcTile - 1) / kTcTile * kTcTile;
+  if (n_total * nd_c + kTcTile >= (1ll << 31) || static_cast<int64_t>(n_queries) * nq + kTcTile >= (1ll << 31))
+    return fail(FLMR_ERR_UNSUPPORTED, "arg-max operands exceed 2^31 rows");
+  // stream-ordered scratch: packed documents, their index maps and lengths (freed in stream order below)
+  const size_t b_dc = static_cast<size_t>(n_total) * nd_c * kDim * 2;
+  const size_t b_map = static_cast<size_t>(n_total) * nd_c * sizeof(int32_t);
+  const size_t b_len = static_cast<size_t>(n_total) * sizeof(int32_t);
+  char* scratch = nullptr;
+  FLMR_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&scratch), b_dc + b_map + b_len + 256, st));
+  uint4* dc = reinterpret_cast<uint4*>(scratch);
+  int32_t* idx_map = reinterpret_cast<int32_t*>(scratch + b_dc);
+  int32_t* doc_len = reinterpret_cast<int32_t*>(scratch + b_dc + b_map);
+  auto done = [&](int code) {
+    cudaFreeAsync(scratch, st);
+    return code;
+  };
+  flmr_compact_docs_kernel<<<static_cast<unsigned>(n_total), 256, 0, st>>>(
+      static_cast<const uint4*>(d_docs), d_mask, nd, nd_c, dc, idx_map, doc_len);
+  ++g_launches;
+  CUtensorMap tmap_q, tmap_d;
+  int rc;
+  if ((rc = encode_rows_map(&tmap_q, d_q, static_cast<uint64_t>(n_queries) * nq, kTcTile))) return done(rc);
+  if ((rc = encode_rows_map(&tmap_d, dc, static_cast<uint64_t>(n_total) * nd_c, kTcTile))) return done(rc);
+  static std::once_flag attr_once[64];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaError_t attr_err = cudaSuccess;
+  std::call_once(attr_once[dev & 63], [&]() {
+    attr_err = cudaFuncSetAttribute(flmr_argmax_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes);
+  });
+  if (attr_err != cudaSuccess)
+    return done(fail(FLMR_ERR_CUDA, "cannot raise the dynamic shared memory limit: %s", cudaGetErrorString(attr_err)));
+  const int n_tiles = (nq + kTcTile - 1) / kTcTile;
+  // documents per CTA: enough to amortise the CTA's set-up (query tile, TMEM allocation, pipeline fill) while
+  // keeping at least one CTA per SM
+  int dpc = 8;
+  while (dpc > 1 && static_cast<int64_t>(n_queries) * n_tiles * ((n_per + dpc - 1) / dpc) < 148) dpc >>= 1;
+  ArgmaxTcParams prm{};
+  prm.doc_len = doc_len;
+  prm.idx_map = idx_map;
+  prm.arg = d_argmax;
+  prm.rowmax = d_rowmax;
+  prm.nq = nq;
+  prm.nd_c = nd_c;
+  prm.n_per = n_per;
+  prm.stride_b = stride_b;
+  prm.docs_per_cta = dpc;
+  prm.status = nullptr;
+  dim3 grid(static_cast<unsigned>((n_per + dpc - 1) / dpc), static_cast<unsigned>(n_tiles),
+            static_cast<unsigned>(n_queries));
+  flmr_argmax_tc_kernel<<<grid, kTcThreads, kTcSmemBytes, st>>>(tmap_q, tmap_d, prm);
+  cudaError_t e = cudaGetLastError();
+  ++g_launches;
+  if (e != cudaSuccess) return done(fail(FLMR_ERR_CUDA, "flmr_argmax_tc_kernel launch failed: %s", cudaGetErrorString(e)));
+  return done(FLMR_OK);
+}
+
 // n_per documents per query; stride_b = 0: all queries meet documents [0, n_per) (all pairs),
 // stride_b = n_per: query b meets documents [b * n_per, (b + 1) * n_per) (block diagonal).
 static int argmax_impl(const void* d_q, int n_queries, int nq, const void* d_docs, const uint8_t* d_mask,
@@ -1473,6 +1537,13 @@ static int argmax_impl(const void* d_q, int n_queries, int nq, const void* d_doc
   if (n_queries == 0 || n_per == 0) return FLMR_OK;
   DeviceGuard guard(device);
   if (!guard.ok) return fail(FLMR_ERR_CUDA, "cudaSetDevice(%d) failed", device);
+  // tcgen05 route when the contraction is worth a TMA / TMEM pipeline (>= 16M query-row x token pairs and full
+  // tiles), warp-MMA kernel below that: a RAG re-score of 5 passages stays on the small kernel
+  const double pairs = static_cast<double>(n_queries) * n_per * nq * nd;
+  const bool tc_ok = n_queries <= 65535 && (nq + kTcTile - 1) / kTcTile <= 65535;
+  if (tc_ok && (g_argmax_path == 2 || (g_argmax_path == 0 && nq >= 64 && nd >= 128 && pairs >= 16e6)))
+    return argmax_tc(d_q, n_queries, nq, d_docs, d_mask, n_per, stride_b, nd, d_argmax, d_rowmax,
+                     static_cast<cudaStream_t>(stream));
   dim3 grid(static_cast<unsigned>((nq + kArgTile - 1) / kArgTile), static_cast<unsigned>(n_per),
             static_cast<unsigned>(n_queries));
 #ifdef FLMR_DEBUG
@@ -1544,6 +1615,27 @@ int flmr_maxsim_backward(const void* d_q, int n_queries, int nq, const void* d_d
   return backward_impl(d_q, n_queries, nq, d_docs, n_docs, 0, nd, d_argmax, d_grad, d_dq, d_dd, device, stream);
 }
 
+int flmr_ib_loss(const float* d_rowmax, int n_queries, int n_docs, int nq, int nway, int label0,
+                 float* d_scores, float* d_loss_per_query, float* d_dscores, int device, void* stream) {
+  if (!d_rowmax || !d_scores || !d_loss_per_query || !d_dscores) return fail(FLMR_ERR_INVALID_ARG, "null pointer");
+  if (n_queries < 1 || n_docs < 1 || nq < 1 || nway < 1 || label0 < 0 ||
+      static_cast<int64_t>(label0) + static_cast<int64_t>(n_queries - 1) * nway >= n_docs)
+    return fail(FLMR_ERR_INVALID_ARG, "bad shape n_queries=%d n_docs=%d nq=%d nway=%d label0=%d", n_queries, n_docs,
+                nq, nway, label0);
+  if (static_cast<size_t>(n_docs) * sizeof(float) > 200 * 1024)
+    return fail(FLMR_ERR_UNSUPPORTED, "%d documents per query exceed the loss kernel's shared memory", n_docs);
+  DeviceGuard guard(device);
+  if (!guard.ok) return fail(FLMR_ERR_CUDA, "cudaSetDevice(%d) failed", device);
+  const size_t smem = static_cast<size_t>(n_docs) * sizeof(float);
+  if (smem > 48 * 1024)
+    FLMR_CUDA(cudaFuncSetAttribute(flmr_ib_loss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  flmr_ib_loss_kernel<<<n_queries, kIbThreads, smem, static_cast<cudaStream_t>(stream)>>>(
+      d_rowmax, n_queries, n_docs, nq, nway, label0, d_scores, d_loss_per_query, d_dscores);
+  FLMR_CUDA(cudaGetLastError());
+  ++g_launches;
+  return FLMR_OK;
+}
+
 int flmr_maxsim_argmax_grouped(const void* d_q, int n_queries, int nq, const void* d_docs,
                                const uint8_t* d_mask, int docs_per_query, int nd, int32_t* d_argmax,
                                float* d_rowmax, int device, void* stream) {
@@ -1575,6 +1667,12 @@ int flmr_debug_maxsim_scores_simt(const flmr_corpus_t* c, const void* d_q, int n
       (flags & FLMR_FLAG_RELU) ? 0.f : -INFINITY, d_out_scores, c->n_passages);
   FLMR_CUDA(cudaGetLastError());
   ++g_launches;
+  return FLMR_OK;
+}
+
+int flmr_debug_set_argmax_path(int path) {
+  if (path < 0 || path > 2) return fail(FLMR_ERR_INVALID_ARG, "path must be 0 (by size), 1 (warp-MMA) or 2 (tcgen05)");
+  g_argmax_path = path;
   return FLMR_OK;
 }
 

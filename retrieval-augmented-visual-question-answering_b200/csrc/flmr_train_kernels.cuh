@@ -290,6 +290,57 @@ __global__ void flmr_bwd_dd_kernel(const __nv_bfloat16* __restrict__ q, const in
   for (int e = 0; e < 4; ++e) atomicAdd(dst + e, gp * f[e]);
 }
 
+// In-batch-negatives loss head (compute_ib_loss_new, CB/modeling/colbert.py:82-113, after the MaxSim matrix):
+// one block per query b.  scores[b, p] = sum_i rowmax[b, p, i] (fixed order: deterministic), then the
+// cross-entropy against the positive at column label0 + b * nway and its gradient
+//     loss_b = logsumexp_p scores[b, p] - scores[b, label_b],   dscores[b, p] = (softmax_p - [p == label_b]) / B
+// — what torch would run as sum + log_softmax + nll_loss forward and their three backward kernels.
+constexpr int kIbThreads = 256;
+__global__ void __launch_bounds__(kIbThreads)
+flmr_ib_loss_kernel(const float* __restrict__ rowmax, int B, int n, int nq, int nway, int label0,
+                    float* __restrict__ scores, float* __restrict__ loss_q, float* __restrict__ dscores) {
+  extern __shared__ float s_sc[];            // [n]
+  __shared__ float s_red[kIbThreads / 32];
+  const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int p = warp; p < n; p += kIbThreads / 32) {
+    const float* r = rowmax + (static_cast<int64_t>(b) * n + p) * nq;
+    float acc = 0.f;
+    for (int i = lane; i < nq; i += 32) acc += r[i];
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if (lane == 0) {
+      s_sc[p] = acc;
+      scores[static_cast<int64_t>(b) * n + p] = acc;
+    }
+  }
+  __syncthreads();
+  float m = -INFINITY;
+  for (int p = tid; p < n; p += kIbThreads) m = fmaxf(m, s_sc[p]);
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+  if (lane == 0) s_red[warp] = m;
+  __syncthreads();
+  m = s_red[0];
+#pragma unroll
+  for (int w = 1; w < kIbThreads / 32; ++w) m = fmaxf(m, s_red[w]);
+  __syncthreads();
+  float se = 0.f;
+  for (int p = tid; p < n; p += kIbThreads) se += expf(s_sc[p] - m);
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) se += __shfl_xor_sync(0xffffffffu, se, off);
+  if (lane == 0) s_red[warp] = se;
+  __syncthreads();
+  se = 0.f;
+#pragma unroll
+  for (int w = 0; w < kIbThreads / 32; ++w) se += s_red[w];
+  const int label = label0 + b * nway;
+  const float lse = m + logf(se);
+  if (tid == 0) loss_q[b] = lse - s_sc[label];
+  const float inv_b = 1.0f / static_cast<float>(B);
+  for (int p = tid; p < n; p += kIbThreads)
+    dscores[static_cast<int64_t>(b) * n + p] = (expf(s_sc[p] - lse) - (p == label ? 1.f : 0.f)) * inv_b;
+}
+
 // Padded batch of retrieved passages out of the resident corpus.  One warp per (slot, token row).
 __global__ void flmr_gather_kernel(const uint2* __restrict__ tokens, const int64_t* __restrict__ poff,
                                    const int32_t* __restrict__ doclen, const int64_t* __restrict__ pids,

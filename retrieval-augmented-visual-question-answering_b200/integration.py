@@ -28,7 +28,7 @@ from typing import Dict, List, Tuple
 
 import torch
 
-from .modeling import all_pairs_maxsim, colbert_score
+from .modeling import all_pairs_maxsim, colbert_score, in_batch_negatives_loss
 from .searcher import Searcher
 
 _undo: List[Tuple[object, str, object]] = []
@@ -62,8 +62,13 @@ def compute_ib_loss_new(self, Q, D, D_mask):
     """ColBERT.compute_ib_loss_new (colbert.py:82-113) as a method replacement: in-batch scores
     ``[B, B*nway]`` from one fused all-pairs launch, positives at column ``i * nway`` (:103-108), the model's
     own ``loss_fn`` (cross-entropy, colbert.py:31)."""
-    scores = all_pairs_maxsim(Q, D, D_mask)
     step = D.shape[0] // Q.shape[0]
+    lf = getattr(self, "loss_fn", None)
+    plain_ce = (isinstance(lf, torch.nn.CrossEntropyLoss) and lf.reduction == "mean" and lf.weight is None
+                and lf.ignore_index == -100 and getattr(lf, "label_smoothing", 0.0) == 0.0)
+    if plain_ce and Q.is_cuda and D.shape[0] == Q.shape[0] * step:
+        return in_batch_negatives_loss(Q, D, D_mask, step)        # arg-max kernel + fused loss head
+    scores = all_pairs_maxsim(Q, D, D_mask)
     labels = torch.arange(Q.shape[0], device=scores.device) * step
     return self.loss_fn(scores, labels)
 

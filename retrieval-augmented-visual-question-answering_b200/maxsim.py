@@ -112,6 +112,24 @@ def _train_operands(Q: torch.Tensor, D_padded: torch.Tensor):
     return (Q.detach().to(torch.bfloat16).contiguous(), D_padded.detach().to(torch.bfloat16).contiguous())
 
 
+def ib_loss_head(rowmax: torch.Tensor, nway: int, label0: int = 0):
+    """``flmr_ib_loss`` on the ``[B, n, Nq]`` row maxima of ``maxsim_argmax``: returns (scores ``[B, n]``, per-query
+    losses ``[B]`` — the in-batch-negatives loss is their mean —, d mean-loss / d scores ``[B, n]``)."""
+    if rowmax.dim() != 3 or rowmax.dtype != torch.float32 or not rowmax.is_cuda:
+        raise ValueError("rowmax must be a CUDA fp32 [B, n, Nq] tensor")
+    r = rowmax.contiguous()
+    B, n, nq = r.shape
+    scores = torch.empty((B, n), dtype=torch.float32, device=r.device)
+    loss_q = torch.empty((B,), dtype=torch.float32, device=r.device)
+    dscores = torch.empty((B, n), dtype=torch.float32, device=r.device)
+    with torch.cuda.device(r.device):
+        _cabi.check(_cabi.lib().flmr_ib_loss(
+            C.c_void_p(r.data_ptr()), B, n, nq, int(nway), int(label0), C.c_void_p(scores.data_ptr()),
+            C.c_void_p(loss_q.data_ptr()), C.c_void_p(dscores.data_ptr()), int(r.device.index),
+            C.c_void_p(torch.cuda.current_stream(r.device).cuda_stream)))
+    return scores, loss_q, dscores
+
+
 def maxsim_argmax_grouped(Q: torch.Tensor, D_padded: torch.Tensor, D_mask: torch.Tensor, docs_per_query: int,
                           return_rowmax: bool = False):
     """Block-diagonal ``maxsim_argmax``: query ``b`` meets only documents ``[b*r, (b+1)*r)``, ``r =

@@ -27,22 +27,24 @@ from typing import Optional
 import torch
 
 from .corpus import FlatCorpus
-from .maxsim import (maxsim_argmax, maxsim_argmax_grouped, maxsim_backward, maxsim_backward_grouped,
-                     maxsim_scores)
+from .maxsim import (ib_loss_head, maxsim_argmax, maxsim_argmax_grouped, maxsim_backward,
+                     maxsim_backward_grouped, maxsim_scores)
 
 
-# Below this many multiply-accumulates the whole forward is ONE launch of the arg-max kernel (scores =
-# row maxima summed), which also saves the winners for the backward; above it the tcgen05 scan kernel over
-# a temporary packed corpus wins despite its per-call setup (allocation, partition build, TMA descriptor:
-# ~2.3 ms measured against ~5e13 MAC/s of the warp-MMA kernel, profiles/r01_train_step_probe.md) and the backward recomputes the winners.
-_FUSED_SMALL_MAX_MACS = 1e11
+# The forward is ONE arg-max launch (scores = row maxima summed) that also saves the winners for the backward —
+# a warp-MMA kernel for small batches, the tcgen05 kernel from 16M (query row, token) pairs up (chosen inside
+# flmr_maxsim_argmax) — as long as the winners + maxima ([B, n, Nq] x 8 bytes) stay below this budget.  Beyond
+# it (an exhaustive evaluation of one query against a whole collection through `score`) the n padded documents
+# are packed into a temporary FlatCorpus and scored by the scan kernel, which keeps nothing per pair; the
+# backward then recomputes the winners.
+_FUSED_MAX_ARG_BYTES = 1 << 30
 
 
 def _forward_scores(Q: torch.Tensor, D_padded: torch.Tensor, D_mask: torch.Tensor):
     """All-pairs scores ``[B, n]``; returns (scores, bool mask [n, Nd], saved arg-max or None)."""
     n, nd = D_padded.size(0), D_padded.size(1)
     mask = D_mask.reshape(n, nd).bool()
-    if float(Q.size(0)) * n * Q.size(1) * nd * Q.size(2) <= _FUSED_SMALL_MAX_MACS:
+    if float(Q.size(0)) * n * Q.size(1) * 8 <= _FUSED_MAX_ARG_BYTES:
         # no host round trip on the training path: a document without any unmasked token scores -inf here
         # (its winners are -1 and it receives no gradient); the reference's padded path gives -9999 * Nq
         arg, rowmax = maxsim_argmax(Q, D_padded, mask, return_rowmax=True)
@@ -148,6 +150,34 @@ def _aligned_maxsim(Q: torch.Tensor, D_padded: torch.Tensor, D_mask: torch.Tenso
     return _GroupedMaxSim.apply(Q, D_padded, D_mask, 1).reshape(n)
 
 
+class _FusedIBLoss(torch.autograd.Function):
+    """compute_ib_loss_new (colbert.py:82-113) in three launches: the arg-max kernel (all-pairs row maxima +
+    winners), ``flmr_ib_loss`` (scores, cross-entropy against the positives at column ``label0 + i * nway``, and
+    the gradient w.r.t. the scores), and — in backward — the gather/scatter kernels.  Returns (loss, scores)."""
+
+    @staticmethod
+    def forward(ctx, Q: torch.Tensor, D_padded: torch.Tensor, D_mask: torch.Tensor, nway: int, label0: int):
+        n, nd = D_padded.size(0), D_padded.size(1)
+        mask = D_mask.reshape(n, nd).bool()
+        Qb, Db = Q.detach().to(torch.bfloat16).contiguous(), D_padded.detach().to(torch.bfloat16).contiguous()
+        arg, rowmax = maxsim_argmax(Qb, Db, mask, return_rowmax=True)
+        scores, loss_q, dscores = ib_loss_head(rowmax, nway, label0)
+        ctx.save_for_backward(Qb, Db, arg, dscores)       # bf16 operands: no second cast in backward
+        ctx.dtypes = (Q.dtype, D_padded.dtype)
+        ctx.mark_non_differentiable(scores)
+        return loss_q.mean(), scores
+
+    @staticmethod
+    def backward(ctx, grad_loss: torch.Tensor, _grad_scores):
+        Qb, Db, arg, dscores = ctx.saved_tensors
+        need_dq, need_dd = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        if not (need_dq or need_dd):
+            return None, None, None, None, None
+        dQ, dD = maxsim_backward(Qb, Db, arg, dscores * grad_loss, need_dq=need_dq, need_dd=need_dd)
+        return (dQ.to(ctx.dtypes[0]) if dQ is not None else None,
+                dD.to(ctx.dtypes[1]) if dD is not None else None, None, None, None)
+
+
 def all_pairs_maxsim(Q: torch.Tensor, D_padded: torch.Tensor, D_mask: torch.Tensor) -> torch.Tensor:
     """``[B, n]`` MaxSim of every query against every padded document (differentiable)."""
     return _AllPairsMaxSim.apply(Q, D_padded, D_mask)
@@ -225,6 +255,11 @@ def in_batch_negatives_loss(Q: torch.Tensor, D_padded: torch.Tensor, D_mask: tor
     score_fn = all_pairs_maxsim if all_pairs_fn is None else all_pairs_fn
     B = Q.size(0)
     assert D_padded.size(0) == B * nway, (D_padded.size(), B, nway)
+    if (all_pairs_fn is None and not cross_rank_negatives and not return_scores and Q.is_cuda
+            and float(B) * D_padded.size(0) * Q.size(1) * 8 <= _FUSED_MAX_ARG_BYTES):
+        # single-rank batch, only the loss wanted (what compute_ib_loss_new returns): arg-max kernel + fused loss
+        # head.  With return_scores the score matrix itself must stay differentiable: generic route below.
+        return _FusedIBLoss.apply(Q, D_padded, D_mask, int(nway), 0)[0]
     first = 0
     if cross_rank_negatives:
         import torch.distributed as dist

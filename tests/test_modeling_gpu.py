@@ -240,3 +240,73 @@ def test_training_path_matches_reference_autograd_golden():
     (s * torch.from_numpy(z["score_weights"]).cuda()).sum().backward()
     np.testing.assert_allclose(Q2.grad.cpu().numpy(), z["score_dQ"], rtol=1e-3, atol=1e-6)
     np.testing.assert_allclose(D2.grad.cpu().numpy(), z["score_dD"], rtol=1e-3, atol=1e-6)
+
+
+@pytest.fixture()
+def argmax_path():
+    """Force flmr_maxsim_argmax onto one of its two kernels for a test (1 = warp-MMA, 2 = tcgen05)."""
+    from ravqa_b200 import _cabi
+    L = _cabi.lib()
+    yield lambda path: _cabi.check(L.flmr_debug_set_argmax_path(path))
+    L.flmr_debug_set_argmax_path(0)
+
+
+@pytest.mark.parametrize("shape", [(3, 70, 5, 83), (2, 320, 7, 300), (1, 832, 9, 512), (4, 129, 3, 128)])
+def test_tcgen05_argmax_kernel_equals_warp_mma_kernel_and_torch(shape, argmax_path):
+    """The tcgen05 arg-max kernel (documents compacted to their unmasked tokens, TMA/TMEM pipeline) against the
+    warp-MMA kernel and torch on the same bf16 inputs: hole-y masks, a fully masked document, a document whose
+    only token sits at the end, sizes off the 128 tiles, several documents per CTA."""
+    from ravqa_b200.maxsim import maxsim_argmax, maxsim_argmax_grouped
+    B, nq, n, nd = shape
+    g = torch.Generator().manual_seed(sum(shape))
+    Q = torch.nn.functional.normalize(torch.randn(B, nq, 128, generator=g), dim=-1).bfloat16().cuda()
+    D = torch.nn.functional.normalize(torch.randn(n, nd, 128, generator=g), dim=-1).bfloat16().cuda()
+    mask = (torch.rand(n, nd, generator=g) > 0.3).cuda()
+    mask[:, 0] = True
+    mask[1] = False                                         # no token at all
+    mask[2] = False
+    mask[2, nd - 1] = True                                  # one token, the last one
+    S = torch.einsum("bqd,pkd->bpqk", Q.float(), D.float()).masked_fill(~mask[None, :, None, :], float("-inf"))
+    argmax_path(1)
+    a1, m1 = maxsim_argmax(Q, D, mask, return_rowmax=True)
+    argmax_path(2)
+    a2, m2 = maxsim_argmax(Q, D, mask, return_rowmax=True)
+    assert a2.dtype == torch.int32 and a2.shape == (B, n, nq)
+    assert (a2[:, 1] == -1).all() and torch.isinf(m2[:, 1]).all() and (a2[:, 2] == nd - 1).all()
+    live = [p for p in range(n) if p != 1]
+    picked = S[:, live].gather(-1, a2[:, live].long().unsqueeze(-1)).squeeze(-1)
+    assert torch.isfinite(picked).all()                                          # never a masked token
+    assert (S[:, live].max(dim=-1).values - picked).abs().max().item() < 1e-5      # ties of the accumulation order at most
+    np.testing.assert_allclose(m2[:, live].cpu().numpy(), S[:, live].max(dim=-1).values.cpu().numpy(), rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(m2[:, live].cpu().numpy(), m1[:, live].cpu().numpy(), rtol=1e-6, atol=1e-6)
+    assert (a1 == a2).float().mean().item() > 0.999
+    # block-diagonal form: query b against documents [b*r, (b+1)*r)
+    if n >= 2 * B:
+        r = n // B
+        Dg, Mg = D[: B * r], mask[: B * r]
+        argmax_path(1)
+        g1, gm1 = maxsim_argmax_grouped(Q, Dg, Mg, r, return_rowmax=True)
+        argmax_path(2)
+        g2, gm2 = maxsim_argmax_grouped(Q, Dg, Mg, r, return_rowmax=True)
+        fin = torch.isfinite(gm1)
+        assert torch.equal(torch.isfinite(gm2), fin) and (g1 == g2).float().mean().item() > 0.999
+        np.testing.assert_allclose(gm2[fin].cpu().numpy(), gm1[fin].cpu().numpy(), rtol=1e-6, atol=1e-6)
+
+
+def test_training_step_on_the_tcgen05_path_matches_golden(argmax_path):
+    """The reference-generated training golden (loss, scores, dQ, dD of compute_ib_loss_new) with the forward
+    forced onto the tcgen05 kernel."""
+    import ravqa_b200 as R
+    from helpers import GOLDEN_DIR
+    import os
+    z = np.load(os.path.join(GOLDEN_DIR, "train_ib_loss.npz"))
+    from helpers import bf16_bits_to_f32
+    Q = torch.from_numpy(bf16_bits_to_f32(z["Q_bf16"])).cuda().requires_grad_(True)
+    D = torch.from_numpy(bf16_bits_to_f32(z["D_bf16"])).cuda().requires_grad_(True)
+    mask = torch.from_numpy(z["mask"]).cuda()
+    argmax_path(2)
+    loss = R.in_batch_negatives_loss(Q, D, mask.unsqueeze(-1), int(z["nway"]))
+    loss.backward()
+    np.testing.assert_allclose(loss.item(), float(z["ib_loss"]), rtol=5e-6)
+    np.testing.assert_allclose(Q.grad.cpu().numpy(), z["ib_dQ"], rtol=1e-3, atol=1e-6)
+    np.testing.assert_allclose(D.grad.cpu().numpy(), z["ib_dD"], rtol=1e-3, atol=1e-6)

@@ -1,6 +1,6 @@
 """Index-load throughput (GPU box): write a synthetic flat index of `--gigabytes` to `--dir` (chunks of 25k
 passages, as the Indexer writes them), drop it from the page cache if allowed, and time FlatCorpus.from_index —
-the C-level streaming builder (pread into two pinned buffers with 4 threads, overlapped H2D, padded layout).
+the C-level streaming builder (pread into two pinned buffers with 8 threads, overlapped H2D, padded layout).
 
     python tools/index_load_probe.py --gigabytes 8 --dir /dev/shm/flmr_idx
 """
