@@ -1502,8 +1502,9 @@ static int argmax_tc(const void* d_q, int n_queries, int nq, const void* d_docs,
   const int n_tiles = (nq + kTcTile - 1) / kTcTile;
   // documents per CTA: enough to amortise the CTA's set-up (query tile, TMEM allocation, pipeline fill) while
   // keeping at least one CTA per SM
-  int dpc = 8;
-  while (dpc > 1 && static_cast<int64_t>(n_queries) * n_tiles * ((n_per + dpc - 1) / dpc) < 148) dpc >>= 1;
+  // (up to 32; at least ~4 CTAs per SM overall so the tail wave stays short)
+  const int64_t doc_tiles = static_cast<int64_t>(n_queries) * n_tiles * n_per;
+  const int dpc = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>({32, n_per, doc_tiles / (148 * 4)})));
   ArgmaxTcParams prm{};
   prm.doc_len = doc_len;
   prm.idx_map = idx_map;

@@ -18,12 +18,19 @@
 //   2. flmr_argmax_tc_kernel: CTA = (query b, 128-row tile of its tokens, a range of documents).  The query tile
 //      is the stationary A operand (TMA -> shared memory once); the CTA streams its documents in chunks of 128
 //      tokens through a 4-stage ring.  Stage s = a 32 KB shared-memory chunk AND a 128-column TMEM accumulator:
-//        warp 4 (producer): TMA, two 128B-swizzled boxes per chunk
-//        warp 5 (issuer)  : 8 x tcgen05.mma (M = 128, N = 128, K = 16), tcgen05.commit -> `done[s]`
-//        warps 0-3        : TMEM lane = query row: each thread walks its row's 128 columns keeping (max, index)
-//                           across the document's chunks; at the document's end one coalesced store per output.
-//      `done[s]` releases the shared-memory chunk to the producer and hands the accumulator to the epilogue;
-//      `t_empty[s]` (one arrive per epilogue warp) hands it back to the issuer.
+//        warp 8 (producer): TMA, two 128B-swizzled boxes per chunk
+//        warp 9 (issuer)  : 8 x tcgen05.mma (M = 128, N = 128, K = 16), tcgen05.commit -> `done[s]`
+//        warps 0-7        : two epilogue warpgroups, documents alternate between them (a document's chunks stay
+//                           with one warpgroup, so its running (max, index) never changes hands).  TMEM lane =
+//                           query row: per 32 columns a compare-select TREE (strict '>' keeps the lower index on
+//                           ties) — 31 independent (FSETP, FSEL, SEL) triples of depth 5 instead of a 32-long
+//                           dependent chain, which with one warp per scheduler ran at a fifth of the MMA rate —
+//                           then one compare against the row's running best; one coalesced store per output at
+//                           the document's end.
+//      Per chunk the issuer commits twice: `free[s]` returns the shared-memory chunk to the producer, `done[g][s]`
+//      hands the accumulator to the warpgroup g that owns the document (one barrier per warpgroup and stage, so
+//      every waiter observes every phase of its barrier); `t_empty[s]` (one arrive per warp of the owner) hands
+//      the accumulator back to the issuer.
 #pragma once
 #include "flmr_device.cuh"
 
@@ -33,7 +40,10 @@ constexpr int kTcTile = 128;                 // query rows per CTA and document 
 constexpr int kTcStages = 4;                 // smem chunks == TMEM accumulator stages (4 x 128 columns)
 constexpr int kTcChunkBytes = kTcTile * 128 * 2;   // 32 KiB: [2 k-blocks][128 rows][64 bf16]
 constexpr int kTcKBlockBytes = kTcTile * 128;      // 16 KiB
-constexpr int kTcThreads = 6 * 32;
+constexpr int kTcEpiWarps = 8;               // two epilogue warpgroups; warpgroup g owns the CTA's documents of parity g
+constexpr int kTcWarpProducer = kTcEpiWarps;
+constexpr int kTcWarpMma = kTcEpiWarps + 1;
+constexpr int kTcThreads = (kTcEpiWarps + 2) * 32;
 constexpr int kTcSmemBytes = (1 + kTcStages) * kTcChunkBytes + 256 + 1024;   // A tile + ring + barriers + align
 
 // grid = total documents; one 256-thread block packs one document.
@@ -96,33 +106,38 @@ flmr_argmax_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
   const uint32_t bar_base = smem_base + (1 + kTcStages) * kTcChunkBytes;
   const uint32_t bar_q = bar_base;
   auto bar_full = [&](int s) { return bar_base + 8u * (1 + s); };
-  auto bar_done = [&](int s) { return bar_base + 8u * (1 + kTcStages + s); };
-  auto bar_tempty = [&](int s) { return bar_base + 8u * (1 + 2 * kTcStages + s); };
-  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + (1 + kTcStages) * kTcChunkBytes + 8 * (1 + 3 * kTcStages));
+  auto bar_free = [&](int s) { return bar_base + 8u * (1 + kTcStages + s); };          // MMA -> producer
+  auto bar_tempty = [&](int s) { return bar_base + 8u * (1 + 2 * kTcStages + s); };    // owner warpgroup -> MMA
+  // accumulator ready, one barrier per (warpgroup, stage): a parity wait only tells CONSECUTIVE phases apart, and
+  // a warpgroup sees only its own documents' chunks, so it needs a barrier whose every phase it observes
+  auto bar_done = [&](int g, int s) { return bar_base + 8u * (1 + 3 * kTcStages + g * kTcStages + s); };
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + (1 + kTcStages) * kTcChunkBytes + 8 * (1 + 5 * kTcStages));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.z, mt = blockIdx.y;
   const int p_begin = blockIdx.x * p.docs_per_cta;
   const int p_end = min(p.n_per, p_begin + p.docs_per_cta);
 
-  if (warp == 4 && lane == 0) {
+  if (warp == kTcWarpProducer && lane == 0) {
     tma_prefetch_desc(&tmap_q);
     tma_prefetch_desc(&tmap_d);
     mbar_init(bar_q, 1);
     for (int s = 0; s < kTcStages; ++s) {
       mbar_init(bar_full(s), 1);
-      mbar_init(bar_done(s), 1);
+      mbar_init(bar_free(s), 1);
+      mbar_init(bar_done(0, s), 1);
+      mbar_init(bar_done(1, s), 1);
       mbar_init(bar_tempty(s), 4);
     }
     mbar_fence_init();
   }
-  if (warp == 5) tmem_alloc<512>(smem_u32(const_cast<uint32_t*>(tmem_ptr_smem)));
+  if (warp == kTcWarpMma) tmem_alloc<512>(smem_u32(const_cast<uint32_t*>(tmem_ptr_smem)));
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
-  if (warp == 4) {
+  if (warp == kTcWarpProducer) {
     // ===================== TMA producer =====================
     if (elect_one_sync()) {
       mbar_arrive_expect_tx(bar_q, kTcChunkBytes);
@@ -138,7 +153,7 @@ flmr_argmax_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
       for (int c = 0; c < nch; ++c, ++n) {
         const int s = n % kTcStages;
         const uint32_t use = n / kTcStages;         // how often this stage was used before
-        if (use > 0) mbar_wait(bar_done(s), (use - 1) & 1u, p.status, kDevTimeoutProducer);
+        if (use > 0) mbar_wait(bar_free(s), (use - 1) & 1u, p.status, kDevTimeoutProducer);
         if (elect_one_sync()) {
           mbar_arrive_expect_tx(bar_full(s), kTcChunkBytes);
           const uint32_t dst = d_smem0 + s * kTcChunkBytes;
@@ -149,7 +164,7 @@ flmr_argmax_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
         __syncwarp();
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == kTcWarpMma) {
     // ===================== MMA issuer =====================
     constexpr uint32_t idesc = make_idesc_bf16_f32(kTcTile, kTcTile);
     mbar_wait(bar_q, 0, p.status, kDevTimeoutMma);
@@ -172,27 +187,34 @@ flmr_argmax_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
             const uint64_t koff = static_cast<uint64_t>(((k >> 2) * kTcKBlockBytes + (k & 3) * 32) >> 4);
             tc_mma_ss(tmem_base + s * kTcTile, a_desc0 + koff, b_desc0 + koff, idesc, k > 0 ? 1u : 0u);
           }
-          tc_commit(bar_done(s));
+          tc_commit(bar_free(s));                               // shared-memory chunk consumed -> producer
+          tc_commit(bar_done((pl - p_begin) & 1, s));           // accumulator complete -> the document's warpgroup
         }
         __syncwarp();
       }
     }
   } else {
     // ===================== epilogue: running (max, index) per query row =====================
-    const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
-    const int i = mt * kTcTile + warp * 32 + lane;               // this thread's query token
+    const int wg = warp >> 2, quad = warp & 3;
+    const uint32_t lane_base = static_cast<uint32_t>(quad * 32) << 16;
+    const int i = mt * kTcTile + quad * 32 + lane;               // this thread's query token
     const bool live = i < p.nq;
     uint32_t n = 0;
+    uint32_t own_parity = 0;                                     // bit s: parity of this warpgroup's next use of stage s
     for (int pl = p_begin; pl < p_end; ++pl) {
       const int64_t pg = static_cast<int64_t>(b) * p.stride_b + pl;
       const int len = __ldg(p.doc_len + pg);
       const int nch = (len + kTcTile - 1) / kTcTile;
+      if (((pl - p_begin) & 1) != wg) {
+        n += nch;                                                // the other warpgroup's document
+        continue;
+      }
       float best = -INFINITY;
       int barg = -1;
       for (int c = 0; c < nch; ++c, ++n) {
         const int s = n % kTcStages;
-        const uint32_t use = n / kTcStages;
-        mbar_wait(bar_done(s), use & 1u, p.status, kDevTimeoutEpilogue);
+        mbar_wait(bar_done(wg, s), (own_parity >> s) & 1u, p.status, kDevTimeoutEpilogue);
+        own_parity ^= 1u << s;
         tc_fence_after_sync();
         const uint32_t taddr = tmem_base + lane_base + s * kTcTile;
         uint32_t v[2][32];
@@ -200,20 +222,37 @@ flmr_argmax_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           FLMR_TMEM_WAIT_LD32(v[q & 1]);
-          if (q < 3) FLMR_TMEM_LD32(v[(q + 1) & 1], taddr + 32 * (q + 1));
-          const int jbase = c * kTcTile + q * 32;
+          if (q < 3) {
+            FLMR_TMEM_LD32(v[(q + 1) & 1], taddr + 32 * (q + 1));
+          } else {                                               // every column is in registers: stage back to the issuer
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_tempty(s));
+          }
+          // compare-select tree over the 32 columns: (value, column) pairs, the lower column wins ties
+          float tv[16];
+          int ti[16];
 #pragma unroll
-          for (int e = 0; e < 32; ++e) {
-            const float x = __uint_as_float(v[q & 1][e]);
-            if (x > best) {          // strict: the first (lowest) index wins ties; pad copies never win
-              best = x;
-              barg = jbase + e;
+          for (int e = 0; e < 16; ++e) {
+            const float x0 = __uint_as_float(v[q & 1][2 * e]), x1 = __uint_as_float(v[q & 1][2 * e + 1]);
+            const bool g1 = x1 > x0;
+            tv[e] = g1 ? x1 : x0;
+            ti[e] = g1 ? 2 * e + 1 : 2 * e;
+          }
+#pragma unroll
+          for (int w = 8; w >= 1; w >>= 1) {
+#pragma unroll
+            for (int e = 0; e < w; ++e) {
+              const bool g1 = tv[2 * e + 1] > tv[2 * e];
+              tv[e] = g1 ? tv[2 * e + 1] : tv[2 * e];
+              ti[e] = g1 ? ti[2 * e + 1] : ti[2 * e];
             }
           }
+          if (tv[0] > best) {                                    // strict: earlier chunks / columns keep ties
+            best = tv[0];
+            barg = c * kTcTile + q * 32 + ti[0];
+          }
         }
-        tc_fence_before_sync();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_tempty(s));
       }
       if (live) {
         const int64_t o = (static_cast<int64_t>(b) * p.n_per + pl) * p.nq + i;
@@ -224,7 +263,7 @@ flmr_argmax_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
     tc_fence_before_sync();
   }
   __syncthreads();
-  if (warp == 5) {
+  if (warp == kTcWarpMma) {
     tc_fence_after_sync();
     tmem_dealloc<512>(tmem_base);
   }

@@ -139,14 +139,14 @@ def test_aligned_score_with_repeat_interleaved_queries():
 
 
 def test_fused_small_forward_and_scan_kernel_forward_agree(monkeypatch):
-    """Training-sized batches take the one-launch arg-max forward, large ones the tcgen05 scan kernel over a
-    packed temporary corpus: same scores (fp32 accumulation of the same bf16 products) and same gradients."""
+    """Batches whose winners fit the memory budget take the one-launch arg-max forward, larger ones the scan kernel
+    over a packed temporary corpus: same scores (fp32 accumulation of the same bf16 products), same gradients."""
     import ravqa_b200 as R
     from ravqa_b200 import modeling
     Q, D, mask = _inputs(5, 96, 9, 77, seed=6)
     outs = []
-    for limit in (modeling._FUSED_SMALL_MAX_MACS, 0.0):
-        monkeypatch.setattr(modeling, "_FUSED_SMALL_MAX_MACS", limit)
+    for limit in (modeling._FUSED_MAX_ARG_BYTES, 0):
+        monkeypatch.setattr(modeling, "_FUSED_MAX_ARG_BYTES", limit)
         Qg, Dg = Q.clone().requires_grad_(True), D.clone().requires_grad_(True)
         S = R.all_pairs_maxsim(Qg, Dg, mask.unsqueeze(-1))
         (S * torch.linspace(-1, 1, S.numel(), device="cuda").view_as(S)).sum().backward()
@@ -310,3 +310,25 @@ def test_training_step_on_the_tcgen05_path_matches_golden(argmax_path):
     np.testing.assert_allclose(loss.item(), float(z["ib_loss"]), rtol=5e-6)
     np.testing.assert_allclose(Q.grad.cpu().numpy(), z["ib_dQ"], rtol=1e-3, atol=1e-6)
     np.testing.assert_allclose(D.grad.cpu().numpy(), z["ib_dD"], rtol=1e-3, atol=1e-6)
+
+
+def test_tcgen05_argmax_many_documents_per_cta_back_to_back(argmax_path):
+    """The global-batch shape (8 queries x 832 rows against 128 ragged documents of up to 512 tokens: 12 documents
+    per CTA, the two epilogue warpgroups alternating documents) launched back to back without synchronisation:
+    same winners and maxima as the warp-MMA kernel every time."""
+    from ravqa_b200.maxsim import maxsim_argmax
+    g = torch.Generator().manual_seed(12)
+    B, nq, n, nd = 8, 832, 128, 512
+    Q = torch.nn.functional.normalize(torch.randn(B, nq, 128, generator=g), dim=-1).bfloat16().cuda()
+    D = torch.nn.functional.normalize(torch.randn(n, nd, 128, generator=g), dim=-1).bfloat16().cuda()
+    lens = torch.randint(1, nd + 1, (n,), generator=g)
+    lens[:4] = torch.tensor([1, 128, 129, 512])
+    mask = (torch.arange(nd)[None, :] < lens[:, None]).cuda()
+    argmax_path(1)
+    a1, m1 = maxsim_argmax(Q, D, mask, return_rowmax=True)
+    argmax_path(2)
+    outs = [maxsim_argmax(Q, D, mask, return_rowmax=True) for _ in range(12)]
+    torch.cuda.synchronize()
+    for a2, m2 in outs:
+        assert torch.equal(m2, m1)
+        assert (a2 == a1).float().mean().item() > 0.9999

@@ -89,6 +89,29 @@ def single_gpu():
         ref_loss(Qg, Dg, m3, nway).backward()
     t_s = timed(step)
     t_r = timed(ref, reps=5)
+    # where the host time of a step goes (CPU-side cost of each call, launches are asynchronous)
+    import time
+    from ravqa_b200 import modeling
+    def host(fn, reps=50):
+        fn(); torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fn()
+        dt = (time.perf_counter() - t0) / reps * 1e3
+        torch.cuda.synchronize()
+        return dt
+    h = {
+        "casts Q,D -> bf16": host(lambda: (Q.detach().to(torch.bfloat16).contiguous(), D.detach().to(torch.bfloat16).contiguous())),
+        "maxsim_argmax (python + C call: cudaMallocAsync, compact, 2 tensor maps, tc kernel, free)": host(lambda: maxsim_argmax(Qb, Db, mask, return_rowmax=True)),
+        "ib_loss_head": host(lambda: ib_loss_head(rowmax, nway)),
+        "maxsim_backward": host(lambda: maxsim_backward(Qb, Db, arg, ds)),
+        "loss.mean + dscores * g": host(lambda: (rowmax[0, 0].mean(), ds * 1.0)),
+        "forward only (autograd function)": host(lambda: R.in_batch_negatives_loss(Qg, Dg, m3, nway)),
+        "whole step": host(step),
+    }
+    print("\n| host-side cost per call | ms |\n|---|---:|")
+    for k, v in h.items():
+        print("| %s | %.3f |" % (k, v))
     print("\n| one rank of the C4 step (8 q x 16 docs) | ms |\n|---|---:|")
     print("| arg-max forward kernel(s) | %.3f |" % t_f)
     print("| loss head kernel (scores, cross-entropy, d loss / d scores) | %.3f |" % t_l)
