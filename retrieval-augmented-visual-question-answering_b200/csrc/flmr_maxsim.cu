@@ -1464,6 +1464,31 @@ int flmr_corpus_gather(const flmr_corpus_t* c, const int64_t* d_pids, int64_t n_
 // ---- the tcgen05 route of the arg-max forward (flmr_train_tc_kernel.cuh) --------------------------------------
 thread_local int g_argmax_path = 0;   // 0 = by size, 1 = warp-MMA kernel, 2 = tcgen05 kernel (flmr_debug_set_argmax_path)
 
+// The library's own stream-ordered memory pool (one per device) for per-call scratch: it keeps what it has
+// been given (release threshold = max), so after the first call an allocation is a pointer bump in stream order —
+// the default pool hands memory back to the driver at every synchronisation and re-maps it on the next call.
+static int scratch_pool(cudaMemPool_t* out) {
+  static cudaMemPool_t pools[64] = {};
+  static std::mutex mu;
+  int dev = 0;
+  FLMR_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(mu);
+  if (!pools[dev & 63]) {
+    cudaMemPoolProps props{};
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = dev;
+    cudaMemPool_t p = nullptr;
+    FLMR_CUDA(cudaMemPoolCreate(&p, &props));
+    uint64_t keep = ~0ull;
+    FLMR_CUDA(cudaMemPoolSetAttribute(p, cudaMemPoolAttrReleaseThreshold, &keep));
+    pools[dev & 63] = p;
+  }
+  *out = pools[dev & 63];
+  return FLMR_OK;
+}
+
 static int argmax_tc(const void* d_q, int n_queries, int nq, const void* d_docs, const uint8_t* d_mask, int n_per,
                      int stride_b, int nd, int32_t* d_argmax, float* d_rowmax, cudaStream_t st) {
   const int64_t n_total = stride_b ? static_cast<int64_t>(n_queries) * n_per : n_per;
@@ -1475,7 +1500,9 @@ static int argmax_tc(const void* d_q, int n_queries, int nq, const void* d_docs,
   const size_t b_map = static_cast<size_t>(n_total) * nd_c * sizeof(int32_t);
   const size_t b_len = static_cast<size_t>(n_total) * sizeof(int32_t);
   char* scratch = nullptr;
-  FLMR_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&scratch), b_dc + b_map + b_len + 256, st));
+  cudaMemPool_t pool = nullptr;
+  if (int rc = scratch_pool(&pool)) return rc;
+  FLMR_CUDA(cudaMallocFromPoolAsync(reinterpret_cast<void**>(&scratch), b_dc + b_map + b_len + 256, pool, st));
   uint4* dc = reinterpret_cast<uint4*>(scratch);
   int32_t* idx_map = reinterpret_cast<int32_t*>(scratch + b_dc);
   int32_t* doc_len = reinterpret_cast<int32_t*>(scratch + b_dc + b_map);
@@ -1500,11 +1527,20 @@ static int argmax_tc(const void* d_q, int n_queries, int nq, const void* d_docs,
   if (attr_err != cudaSuccess)
     return done(fail(FLMR_ERR_CUDA, "cannot raise the dynamic shared memory limit: %s", cudaGetErrorString(attr_err)));
   const int n_tiles = (nq + kTcTile - 1) / kTcTile;
-  // documents per CTA: enough to amortise the CTA's set-up (query tile, TMEM allocation, pipeline fill) while
-  // keeping at least one CTA per SM
-  // (up to 32; at least ~4 CTAs per SM overall so the tail wave stays short)
-  const int64_t doc_tiles = static_cast<int64_t>(n_queries) * n_tiles * n_per;
-  const int dpc = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>({32, n_per, doc_tiles / (148 * 4)})));
+  // documents per CTA: a CTA pays ~5 us of set-up (TMEM allocation, barriers, query tile, pipeline fill) before its
+  // first MMA and ~0.3 us per 128-token chunk after it; pick the split with the shortest modelled makespan
+  // (waves of 148 CTAs x per-CTA time): many documents per CTA unless that leaves SMs idle
+  const int64_t pairs_q = static_cast<int64_t>(n_queries) * n_tiles;
+  int dpc = 1;
+  double best_t = 1e30;
+  for (int d = 1; d <= 32 && d <= std::max(1, n_per); ++d) {
+    const int64_t ctas = pairs_q * ((n_per + d - 1) / d);
+    const double t = static_cast<double>((ctas + 147) / 148) * (5.0 + d * 0.3 * (nd_c / kTcTile));
+    if (t < best_t) {
+      best_t = t;
+      dpc = d;
+    }
+  }
   ArgmaxTcParams prm{};
   prm.doc_len = doc_len;
   prm.idx_map = idx_map;
