@@ -53,19 +53,40 @@ class Indexer:
     def _path(self, name: str) -> str:
         return name if (os.path.isabs(name) or self.index_root is None) else os.path.join(self.index_root, name)
 
+    def _barrier(self) -> None:
+        """All ranks of a multi-rank build meet here.  The reference erases and plans in the parent process before
+        it launches the workers (colbert/indexer.py:58-84); ranks that call ``index`` independently need the same
+        ordering, so a multi-rank build requires an initialised ``torch.distributed`` process group."""
+        if self.nranks > 1:
+            if not (torch.distributed.is_available() and torch.distributed.is_initialized()):
+                raise RuntimeError("Indexer(nranks=%d) needs an initialised torch.distributed process group: rank 0 "
+                                   "erases / finalizes, the others must wait for it" % self.nranks)
+            torch.distributed.barrier()
+
     def index(self, name: str, collection: Sequence, overwrite=False) -> str:
         assert overwrite in [True, False, "reuse", "resume"]
         if self.encode_fn is None:
             raise RuntimeError("Indexer needs encode_fn=...: the document encoder (ColBERT.doc / "
                                "Checkpoint.docFromText) stays in PyTorch and is out of scope here")
         self.index_path = self._path(name)
-        exists = os.path.exists(os.path.join(self.index_path, "metadata.json")) or (
-            os.path.isdir(self.index_path) and len(os.listdir(self.index_path)) > 0)
-        assert overwrite in [True, "reuse", "resume"] or not exists, self.index_path
-        os.makedirs(self.index_path, exist_ok=True)
-        if overwrite is True and self.rank == 0:
-            self.erase()
-        if exists and overwrite == "reuse" and os.path.exists(os.path.join(self.index_path, "metadata.json")):
+        # rank 0 decides about the directory (exists? erase?) BEFORE any rank writes a chunk into it; the others
+        # wait at the barrier, so a fast rank can neither have its chunks erased nor trip the exists-check
+        reuse = False
+        if self.rank == 0:
+            exists = os.path.exists(os.path.join(self.index_path, "metadata.json")) or (
+                os.path.isdir(self.index_path) and len(os.listdir(self.index_path)) > 0)
+            assert overwrite in [True, "reuse", "resume"] or not exists, self.index_path
+            os.makedirs(self.index_path, exist_ok=True)
+            if overwrite is True:
+                self.erase()
+            reuse = bool(exists and overwrite == "reuse"
+                         and os.path.exists(os.path.join(self.index_path, "metadata.json")))
+        if self.nranks > 1:
+            self._barrier()
+            flag = [reuse]
+            torch.distributed.broadcast_object_list(flag, src=0)
+            reuse = flag[0]
+        if reuse:
             return self.index_path
         self._encode(collection, resume=(overwrite == "resume"))
         return self.index_path
@@ -105,7 +126,7 @@ class Indexer:
             th.join()
         if errors:
             raise errors[0]
-        if torch.distributed.is_available() and torch.distributed.is_initialized() and self.nranks > 1:
-            torch.distributed.barrier()
+        self._barrier()                                   # every rank's chunks are on disk
         if self.rank == 0:
             finalize_chunked_index(self.index_path, num_chunks)
+        self._barrier()                                   # nobody returns before metadata.json exists

@@ -299,7 +299,13 @@ class FLMRModelForRetrieval(torch.nn.Module):
         return self.doc_encoder(*args, **kw)
 
     def score(self, Q: torch.Tensor, D_padded: torch.Tensor, D_mask: torch.Tensor) -> torch.Tensor:
-        """ColBERT.score (colbert.py:217-224), similarity == 'cosine'."""
+        """ColBERT.score (colbert.py:217-224).  ``similarity == 'cosine'`` (what FLMR uses, settings.py:118) runs
+        on the CUDA path; the ``'l2'`` branch of the reference (:219-222, unused by FLMR: negative squared
+        distance, no masking) is kept as the same torch expression so a config that selects it still works."""
+        cfg = getattr(self, "colbert_config", None)
+        if cfg is not None and getattr(cfg, "similarity", "cosine") == "l2":
+            assert getattr(cfg, "interaction", "colbert") == "colbert"
+            return (-1.0 * ((Q.unsqueeze(2) - D_padded.unsqueeze(1)) ** 2).sum(-1)).max(-1).values.sum(-1)
         return colbert_score(Q, D_padded, D_mask)
 
     def forward(self, Q: torch.Tensor, D: torch.Tensor, D_mask: torch.Tensor):

@@ -333,11 +333,27 @@ class Searcher:
         return {"doc_scores": doc_scores, "retrieved_doc_ids": p.cpu().numpy(), "search_scores": s,
                 "item_embeddings": D, "item_mask": mask}
 
+    def _fill_search_knobs(self, k: int) -> None:
+        """searcher.py:92-118: the first search fills the PLAID knobs still unset on ``config`` from ``k`` (and later
+        searches keep them).  They steer nothing here — the scan is exhaustive — but callers that read
+        ``searcher.config.ncells`` etc. after a search find what the reference would have left there."""
+        cfg = self.config
+        if cfg is None or not hasattr(cfg, "configure") or not hasattr(cfg, "ncells"):
+            return
+        ncells, thr, ndocs = (2, 0.45, 1024) if k <= 100 else (4, 0.4, max(k * 4, 4096))
+        if cfg.ncells is None:
+            cfg.configure(ncells=ncells)
+        if cfg.centroid_score_threshold is None:
+            cfg.configure(centroid_score_threshold=thr)
+        if cfg.ndocs is None:
+            cfg.configure(ndocs=ndocs)
+
     def dense_search(self, Q: torch.Tensor, k: int = 10, filter_fn=None, remove_zero_tensors: bool = False):
         """searcher.py:91-132 -> ``(pids[:k], [1..k], scores[:k])`` for ONE query ``Q [1, Nq, d]``."""
         if Q.dim() == 2:
             Q = Q.unsqueeze(0)
         assert Q.size(0) == 1, "dense_search takes a single query (use _search_all_Q for batches)"
+        self._fill_search_knobs(k)
         s, p = self._search_tensors(Q, k, filter_fn, remove_zero_tensors)
         pids, scores = p[0].tolist(), s[0].tolist()
         return pids, list(range(1, len(pids) + 1)), scores
@@ -347,6 +363,7 @@ class Searcher:
         """searcher.py:73-89, batched: one fused scan per ``query_batch`` queries instead of a Python
         loop of per-query ``dense_search`` calls."""
         del progress
+        self._fill_search_knobs(k)
         keys = _query_keys(queries, Q.size(0))
         s, p = self._search_tensors(Q, k, filter_fn, remove_zero_tensors)
         s, p = s.cpu().tolist(), p.cpu().tolist()

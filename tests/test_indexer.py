@@ -2,6 +2,7 @@
 resume), chunk ownership across ranks, shard-range loading."""
 import json
 import os
+import zlib
 
 import numpy as np
 import pytest
@@ -20,7 +21,7 @@ def fake_encoder(calls):
         # make embeddings a pure function of the passage text so chunks are reproducible
         rows = []
         for p, n in zip(passages, doclens):
-            gp = torch.Generator().manual_seed(hash(p) % (2 ** 31))
+            gp = torch.Generator().manual_seed(zlib.crc32(p.encode()))    # (str hashes differ between processes)
             rows.append(torch.nn.functional.normalize(torch.randn(n, 128, generator=gp), dim=-1))
         return torch.cat(rows), doclens
     return encode
@@ -54,11 +55,40 @@ def test_index_chunks_resume_and_load(tmp_path):
     assert torch.equal(t3, tokens) and d3.tolist() == ref_d
 
 
-def test_round_robin_ranks_and_single_file_format(tmp_path):
+def _two_rank_worker(rank, port, root, ret):
+    import time
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=2)
     passages = ["p%d" % i for i in range(90)]
-    for rank in (1, 0):                                # rank 0 last: it finalizes
-        Indexer(encode_fn=fake_encoder([]), index_root=str(tmp_path), chunksize=20, rank=rank, nranks=2
-                ).index("idx", passages, overwrite="resume")
+    if rank == 0:
+        time.sleep(1.0)          # rank 1 reaches index() first: it must wait for rank 0's erase, not be erased by it
+    ix = Indexer(encode_fn=fake_encoder([]), index_root=root, chunksize=20, rank=rank, nranks=2)
+    path = ix.index("idx", passages, overwrite=True)
+    ret[rank] = os.path.exists(os.path.join(path, "metadata.json"))      # nobody returns before the index is final
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_round_robin_ranks_and_single_file_format(tmp_path):
+    """Two ranks build one index (round-robin chunk ownership) over a directory that already holds a stale index:
+    rank 0 erases and finalizes, rank 1 waits for the erase and rank 0 for rank 1's chunks (the reference does the
+    erase in the parent before launching its workers, colbert/indexer.py:58-84)."""
+    import socket
+    import torch.multiprocessing as mp
+    passages = ["p%d" % i for i in range(90)]
+    stale = os.path.join(str(tmp_path), "idx")
+    save_flat_index(stale, torch.zeros(7, 128), [3, 4])                   # what overwrite=True must remove
+    sock = socket.socket()
+    sock.bind(("127.0.0.1", 0))
+    port = sock.getsockname()[1]
+    sock.close()
+    ret = mp.Manager().dict()
+    mp.spawn(_two_rank_worker, args=(port, str(tmp_path), ret), nprocs=2, join=True)
+    assert dict(ret) == {0: True, 1: True}
+    with pytest.raises(RuntimeError, match="process group"):              # ranks cannot be faked one after the other
+        Indexer(encode_fn=fake_encoder([]), index_root=str(tmp_path), rank=1, nranks=2).index("y", passages)
     tokens, doclens, meta = load_flat_index(os.path.join(str(tmp_path), "idx"))
     ref_t, ref_d = fake_encoder([])(passages)
     assert meta["num_chunks"] == 5 and doclens.tolist() == ref_d and torch.equal(tokens, ref_t.to(torch.bfloat16))
