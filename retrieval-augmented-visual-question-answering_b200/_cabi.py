@@ -42,7 +42,7 @@ SYMBOLS = [
     "flmr_corpus_builder_finish", "flmr_corpus_builder_destroy",
     "flmr_comm_unique_id", "flmr_comm_create", "flmr_comm_adopt", "flmr_comm_destroy", "flmr_comm_info",
     "flmr_topk_exchange", "flmr_maxsim_topk_sharded",
-    "flmr_debug_maxsim_scores_simt", "flmr_debug_set_argmax_path", "flmr_debug_build_partition", "flmr_debug_plan_passes",
+    "flmr_debug_maxsim_scores_simt", "flmr_debug_set_argmax_path", "flmr_debug_set_scan_variant", "flmr_debug_build_partition", "flmr_debug_plan_passes",
     "flmr_launch_count", "flmr_set_profiling", "flmr_scan_kernel_stats",
 ]
 
@@ -108,6 +108,7 @@ def lib() -> C.CDLL:
     L.flmr_maxsim_topk_sharded.argtypes = [vp, vp, vp, vp, i32, i32, i32, u32, vp, vp, vp]
     L.flmr_debug_maxsim_scores_simt.argtypes = [vp, vp, i32, i32, u32, vp, vp]
     L.flmr_debug_set_argmax_path.argtypes = [i32]
+    L.flmr_debug_set_scan_variant.argtypes = [i32]
     L.flmr_debug_build_partition.argtypes = [vp, i64, i32, vp, vp, vp, vp, i64, C.POINTER(i64)]
     L.flmr_debug_plan_passes.argtypes = [i32, i32, vp, i32, C.POINTER(i32)]
     L.flmr_launch_count.restype = i64

@@ -30,6 +30,7 @@
 
 #include "../../include/flmr_maxsim.h"
 #include "flmr_scan_kernel.cuh"
+#include "flmr_scan3_kernel.cuh"
 #include "flmr_train_kernels.cuh"
 #include "flmr_train_tc_kernel.cuh"
 
@@ -624,6 +625,10 @@ int load_nccl(const NcclApi** out) {
 constexpr int kNcclInt64 = 4, kNcclFloat32 = 7;   // ncclDataType_t values (nccl.h: ncclInt64 = 4, ncclFloat32 = 7)
 
 thread_local bool g_profiling = false;
+// which scan kernel a search on this thread launches: 0 = the default below, 2 = flmr_scan_kernel (two epilogue
+// warpgroups), 3 = flmr_scan3_kernel (three, static query-tile assignment); flmr_debug_set_scan_variant
+thread_local int g_scan_variant = 0;
+constexpr int kDefaultScanVariant = 2;
 struct EventPair {
   cudaEvent_t a, b;
 };
@@ -736,10 +741,13 @@ void plan_passes(int n_queries, int nq, std::vector<PassPlan>* out, int* group_o
 int launch_scan(const flmr_corpus* c, flmr_workspace* ws, const ScanParams& p, cudaStream_t st) {
   // product instantiation unless a timing experiment / timestamp mode was requested
   // (both instantiations got their dynamic-shared-memory limit raised in flmr_corpus_create)
+  const bool three = (g_scan_variant == 3) || (g_scan_variant == 0 && kDefaultScanVariant == 3);
 #ifdef FLMR_DEBUG
   auto kern = p.debug_mode ? flmr_scan_kernel<true> : flmr_scan_kernel<false>;
+  const bool use3 = three && !p.debug_mode;
 #else
   auto kern = flmr_scan_kernel<false>;
+  const bool use3 = three;
 #endif
   EventPair ev{};
   if (g_profiling) {
@@ -748,7 +756,10 @@ int launch_scan(const flmr_corpus* c, flmr_workspace* ws, const ScanParams& p, c
     FLMR_CUDA(cudaEventRecord(ev.a, st));
   }
   (void)ws;
-  kern<<<c->n_ctas, kScanThreads, ScanSmem::kBytes, st>>>(c->tmap_d, p);
+  if (use3)
+    flmr_scan3_kernel<<<c->n_ctas, kScan3Threads, ScanSmem::kBytes, st>>>(c->tmap_d, p);
+  else
+    kern<<<c->n_ctas, kScanThreads, ScanSmem::kBytes, st>>>(c->tmap_d, p);
   FLMR_CUDA(cudaGetLastError());
   ++g_launches;
   if (g_profiling) {
@@ -932,6 +943,8 @@ int finish_corpus(flmr_corpus* c, const std::vector<int64_t>& poff, const int32_
   {  // per-device function attribute, set here (idempotent) rather than at launch time
     cudaError_t e1 = cudaFuncSetAttribute(flmr_scan_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           ScanSmem::kBytes);
+    if (e1 == cudaSuccess)
+      e1 = cudaFuncSetAttribute(flmr_scan3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ScanSmem::kBytes);
 #ifdef FLMR_DEBUG
     cudaError_t e2 = cudaFuncSetAttribute(flmr_scan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           ScanSmem::kBytes);
@@ -1704,6 +1717,13 @@ int flmr_debug_maxsim_scores_simt(const flmr_corpus_t* c, const void* d_q, int n
       (flags & FLMR_FLAG_RELU) ? 0.f : -INFINITY, d_out_scores, c->n_passages);
   FLMR_CUDA(cudaGetLastError());
   ++g_launches;
+  return FLMR_OK;
+}
+
+int flmr_debug_set_scan_variant(int variant) {
+  if (variant != 0 && variant != 2 && variant != 3)
+    return fail(FLMR_ERR_INVALID_ARG, "variant must be 0 (default), 2 or 3 (epilogue warpgroups)");
+  g_scan_variant = variant;
   return FLMR_OK;
 }
 

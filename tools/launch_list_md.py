@@ -27,7 +27,7 @@ def main():
         n, t = agg.get(short, (0, 0.0))
         agg[short] = (n + 1, t + ms)
     total = sum(t for _, t in agg.values())
-    print("# ncu launch list, round 1 (final kernel)\n")
+    print("# ncu launch list\n")
     print("Command (B200, 1 GPU): `%s`\n" % command)
     print("Per-launch times under ncu are cold-cache and serialised: compare SHARES, not absolutes. Includes corpus "
           "generation (torch randn/normalize), the bench's HBM-regime leg, its self-check and the library-GPU "
