@@ -298,9 +298,10 @@ int flmr_maxsim_backward_grouped(const void* d_q, int n_queries, int nq, const v
 int flmr_debug_maxsim_scores_simt(const flmr_corpus_t* corpus, const void* d_q, int n_queries,
                                   int nq, unsigned flags, float* d_out_scores, void* stream);
 
-/* Test infrastructure: which scan kernel searches on the calling thread launch — 0 = the library's default,
+/* Test infrastructure: which scan kernel searches on the calling thread launch — 0 = chosen per pass (the product
+ * behaviour: three epilogue warpgroups for passes with three resident query tiles, two otherwise),
  * 2 = flmr_scan_kernel (two epilogue warpgroups), 3 = flmr_scan3_kernel (three, static query-tile assignment) —
- * so the parity suite can run against either. */
+ * so the parity suite can run against either at any shape. */
 int flmr_debug_set_scan_variant(int variant);
 
 /* Test infrastructure: which kernel flmr_maxsim_argmax(_grouped) runs on the calling thread — 0 = chosen by size

@@ -625,10 +625,9 @@ int load_nccl(const NcclApi** out) {
 constexpr int kNcclInt64 = 4, kNcclFloat32 = 7;   // ncclDataType_t values (nccl.h: ncclInt64 = 4, ncclFloat32 = 7)
 
 thread_local bool g_profiling = false;
-// which scan kernel a search on this thread launches: 0 = the default below, 2 = flmr_scan_kernel (two epilogue
-// warpgroups), 3 = flmr_scan3_kernel (three, static query-tile assignment); flmr_debug_set_scan_variant
+// which scan kernel a search on this thread launches: 0 = chosen per pass (launch_scan), 2 = flmr_scan_kernel (two
+// epilogue warpgroups), 3 = flmr_scan3_kernel (three, static query-tile assignment); flmr_debug_set_scan_variant
 thread_local int g_scan_variant = 0;
-constexpr int kDefaultScanVariant = 2;
 struct EventPair {
   cudaEvent_t a, b;
 };
@@ -741,7 +740,11 @@ void plan_passes(int n_queries, int nq, std::vector<PassPlan>* out, int* group_o
 int launch_scan(const flmr_corpus* c, flmr_workspace* ws, const ScanParams& p, cudaStream_t st) {
   // product instantiation unless a timing experiment / timestamp mode was requested
   // (both instantiations got their dynamic-shared-memory limit raised in flmr_corpus_create)
-  const bool three = (g_scan_variant == 3) || (g_scan_variant == 0 && kDefaultScanVariant == 3);
+  // three epilogue warpgroups pay off exactly where they buy a third TMEM accumulator stage and one accumulator
+  // per warpgroup and D tile: passes with three resident query tiles (one Nq = 320 query: +12 %, 66 -> 74.5 q/s at
+  // 1M passages); with five tiles (2 / 2 / 1 accumulators per warpgroup, still two stages) they measured 7 % slower
+  // than strict two-warpgroup alternation, with one, two or four tiles the same (profiles/r02_scan_variant_probe.md)
+  const bool three = (g_scan_variant == 3) || (g_scan_variant == 0 && p.n_mtiles == 3);
 #ifdef FLMR_DEBUG
   auto kern = p.debug_mode ? flmr_scan_kernel<true> : flmr_scan_kernel<false>;
   const bool use3 = three && !p.debug_mode;

@@ -276,3 +276,33 @@ def test_topk_select_kernel(R):
         assert np.array_equal(vs.cpu().numpy(), rs), (n, k)
     with pytest.raises(ValueError):
         R.topk_select(torch.zeros(2, 10, device="cuda"), 4096)
+
+
+@pytest.mark.parametrize("case", [
+    (3000, 60, 1, 32, True, False, 5), (3000, 60, 2, 64, True, True, 7), (2000, 180, 1, 320, False, False, 5),
+    (2000, 180, 2, 320, True, False, 100), (1500, 90, 3, 129, True, False, 5), (1200, 100, 5, 97, True, False, 3),
+    (900, 64, 20, 32, True, False, 5), (700, 50, 3, 832, True, False, 10), (5, 7, 2, 320, True, False, 5),
+    (2500, 13, 2, 320, True, False, 5), (800, 200, 16, 320, True, False, 5)])
+def test_three_warpgroup_scan_kernel_is_bit_identical(case):
+    """flmr_scan3_kernel (three epilogue warpgroups, static query-tile assignment, 2-4 TMEM stages; the product
+    uses it for passes with three resident query tiles) forced onto every pass shape: scores and fused top-k
+    bit-identical to flmr_scan_kernel's and within 2e-5 of the oracle."""
+    import ravqa_b200 as R
+    from ravqa_b200 import _cabi
+    n, nd, B, nq, ragged, relu, k = case
+    L = _cabi.lib()
+    Q, D, dl = O.synth(n, nd, B, nq, seed=n + nq, ragged=ragged)
+    corpus = R.FlatCorpus(torch.from_numpy(D).to(torch.bfloat16), dl, device=0)
+    Qt = torch.from_numpy(Q)
+    try:
+        outs = {}
+        for variant in (2, 3, 0):
+            _cabi.check(L.flmr_debug_set_scan_variant(variant))
+            outs[variant] = (R.maxsim_scores(corpus, Qt, relu=relu), *R.maxsim_topk(corpus, Qt, min(k, n), relu=relu))
+    finally:
+        L.flmr_debug_set_scan_variant(0)
+    for variant in (3, 0):
+        for x, y in zip(outs[2], outs[variant]):
+            assert torch.equal(x, y)
+    ref = O.maxsim_scores(Q, D, dl, relu=relu)
+    np.testing.assert_allclose(outs[3][0].cpu().numpy(), ref, rtol=2e-5)
