@@ -44,7 +44,7 @@ constexpr int kTcEpiWarps = 8;               // two epilogue warpgroups; warpgro
 constexpr int kTcWarpProducer = kTcEpiWarps;
 constexpr int kTcWarpMma = kTcEpiWarps + 1;
 constexpr int kTcThreads = (kTcEpiWarps + 2) * 32;
-constexpr int kTcSmemBytes = (1 + kTcStages) * kTcChunkBytes + 256 + 1024;   // A tile + ring + barriers + align
+constexpr int kTcSmemBytes = (1 + kTcStages) * kTcChunkBytes + 512 + 1024;   // A tile + ring + barriers, lengths + align
 
 // grid = total documents; one 256-thread block packs one document.
 __global__ void __launch_bounds__(256)
@@ -112,6 +112,9 @@ flmr_argmax_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
   // a warpgroup sees only its own documents' chunks, so it needs a barrier whose every phase it observes
   auto bar_done = [&](int g, int s) { return bar_base + 8u * (1 + 3 * kTcStages + g * kTcStages + s); };
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + (1 + kTcStages) * kTcChunkBytes + 8 * (1 + 5 * kTcStages));
+  // lengths of this CTA's documents, read from global memory ONCE (every role walks the same document list; a
+  // global load per document and role put ~500 cycles of latency in front of each document's first chunk)
+  int32_t* s_len = reinterpret_cast<int32_t*>(smem + (1 + kTcStages) * kTcChunkBytes + 8 * (1 + 5 * kTcStages) + 16);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.z, mt = blockIdx.y;
@@ -132,6 +135,8 @@ flmr_argmax_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
     mbar_fence_init();
   }
   if (warp == kTcWarpMma) tmem_alloc<512>(smem_u32(const_cast<uint32_t*>(tmem_ptr_smem)));
+  if (warp == 0 && p_begin + lane < p_end)
+    s_len[lane] = __ldg(p.doc_len + static_cast<int64_t>(b) * p.stride_b + p_begin + lane);   // docs_per_cta <= 32
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
@@ -149,7 +154,7 @@ flmr_argmax_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
     uint32_t n = 0;                                 // chunks issued so far
     for (int pl = p_begin; pl < p_end; ++pl) {
       const int64_t pg = static_cast<int64_t>(b) * p.stride_b + pl;
-      const int nch = (__ldg(p.doc_len + pg) + kTcTile - 1) / kTcTile;
+      const int nch = (s_len[pl - p_begin] + kTcTile - 1) / kTcTile;
       for (int c = 0; c < nch; ++c, ++n) {
         const int s = n % kTcStages;
         const uint32_t use = n / kTcStages;         // how often this stage was used before
@@ -172,8 +177,7 @@ flmr_argmax_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
     const uint64_t a_desc0 = make_kmajor_sw128_desc(a_smem);
     uint32_t n = 0;
     for (int pl = p_begin; pl < p_end; ++pl) {
-      const int64_t pg = static_cast<int64_t>(b) * p.stride_b + pl;
-      const int nch = (__ldg(p.doc_len + pg) + kTcTile - 1) / kTcTile;
+      const int nch = (s_len[pl - p_begin] + kTcTile - 1) / kTcTile;
       for (int c = 0; c < nch; ++c, ++n) {
         const int s = n % kTcStages;
         const uint32_t use = n / kTcStages;
@@ -203,7 +207,7 @@ flmr_argmax_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
     uint32_t own_parity = 0;                                     // bit s: parity of this warpgroup's next use of stage s
     for (int pl = p_begin; pl < p_end; ++pl) {
       const int64_t pg = static_cast<int64_t>(b) * p.stride_b + pl;
-      const int len = __ldg(p.doc_len + pg);
+      const int len = s_len[pl - p_begin];
       const int nch = (len + kTcTile - 1) / kTcTile;
       if (((pl - p_begin) & 1) != wg) {
         n += nch;                                                // the other warpgroup's document
