@@ -306,3 +306,26 @@ def test_three_warpgroup_scan_kernel_is_bit_identical(case):
             assert torch.equal(x, y)
     ref = O.maxsim_scores(Q, D, dl, relu=relu)
     np.testing.assert_allclose(outs[3][0].cpu().numpy(), ref, rtol=2e-5)
+
+
+def test_c2_shape_against_the_c_oracle():
+    """BASELINE.json configs[1] (PreFLMR ViT-B on OK-VQA's GoogleSearch corpus) at its exact query shape — the full
+    832-row FLMR query (512 text + 320 vision rows), row-sliced over passes, k = max(Ks) = 100
+    (FLMR_base_preload_vision_features.jsonnet:141) — over a 2,000-passage ragged slice (90..180 tokens), against the
+    plain-C oracle: scores within 2e-5, the 100 ids identical."""
+    import ravqa_b200 as R
+    from helpers import c_oracle_scores
+    rng = np.random.default_rng(77)
+    n, nq, B, k = 2000, 832, 3, 100
+    dl = rng.integers(90, 181, size=n).astype(np.int32)
+    g = torch.Generator().manual_seed(77)
+    D = torch.nn.functional.normalize(torch.randn(int(dl.sum()), 128, generator=g), dim=-1).bfloat16().float().numpy()
+    Q = torch.nn.functional.normalize(torch.randn(B, nq, 128, generator=g), dim=-1).bfloat16().float().numpy()
+    corpus = R.FlatCorpus(torch.from_numpy(D).to(torch.bfloat16), dl, device=0)
+    ref = c_oracle_scores(Q, D, dl, nthreads=8)
+    got = R.maxsim_scores(corpus, torch.from_numpy(Q)).cpu().numpy()
+    np.testing.assert_allclose(got, ref, rtol=2e-5)
+    s, p = R.Searcher(index=corpus)._search_tensors(torch.from_numpy(Q), k)
+    rs, rp = O.topk(ref, k)
+    assert np.array_equal(p.cpu().numpy(), rp)
+    np.testing.assert_allclose(s.cpu().numpy(), rs, rtol=2e-5)
