@@ -602,6 +602,16 @@ def run_ours(args):
         except Exception as e:
             lib_gpu = {"value": None, "unit": UNIT, "kind": "error", "sample": repr(e)}
 
+    # ---- C4-shaped record (BASELINE.json configs[3]: contrastive step, in-batch negatives, bsz 64 on 8 GPUs = 8
+    # queries x 16 documents per rank, Nq = 832, Nd = 512): the MaxSim loss step (forward + backward) of one rank,
+    # and with N > 1 the same with cross-rank negatives (all-gather of the documents, [8, N*16] matrix per rank,
+    # all-reduce of dD; CB/modeling/colbert.py:64-113, 115-163).  Max over ranks of CUDA-event time.
+    c4 = None
+    try:
+        c4 = c4_record(dev, world, rank)
+    except Exception as e:
+        c4 = {"kind": "error", "sample": repr(e)}
+
     # ---- C2-shaped record (BASELINE.json configs[1]: PreFLMR ViT-B on OK-VQA's 112k-passage corpus): ragged
     # passages, the full 832-row FLMR query (512 text + 320 vision rows, row-sliced over passes), k = max(Ks) = 100
     c2 = None
@@ -684,6 +694,8 @@ def run_ours(args):
             line["library_gpu_baseline"] = lib_gpu
         if c2:
             line["c2"] = c2
+        if c4:
+            line["c4_loss_step"] = c4
         if world == 1 and not args.no_cpu_baseline and not args.no_plaid_baseline:
             try:
                 line["cpu_baseline_plaid"] = cpu_plaid_rate(args, "cuda:%d" % local_rank)
@@ -697,6 +709,47 @@ def run_ours(args):
     if not ok:
         raise SystemExit("bench parity check failed: recall@1=%.3f self_check=%s e2e_same=%s"
                          % (recall_1, self_check, e2e_same))
+
+
+def c4_record(dev, world, rank):
+    import torch
+    import torch.distributed as dist
+    import ravqa_b200 as R
+    B, nway, nq, nd = 8, 2, 832, 512
+    g = torch.Generator().manual_seed(1000 + rank)
+    Q = torch.nn.functional.normalize(torch.randn(B, nq, 128, generator=g), dim=-1).to(dev).requires_grad_(True)
+    D = torch.nn.functional.normalize(torch.randn(B * nway, nd, 128, generator=g), dim=-1).to(dev).requires_grad_(True)
+    lens = torch.randint(nd // 2, nd + 1, (B * nway,), generator=g)
+    mask = (torch.arange(nd)[None, :] < lens[:, None]).unsqueeze(-1).to(dev)
+
+    def timed(cross, reps=20):
+        def step():
+            Q.grad = D.grad = None
+            R.in_batch_negatives_loss(Q, D, mask, nway, cross_rank_negatives=cross).backward()
+        for _ in range(3):
+            step()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            step()
+        b.record()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        t = torch.tensor([a.elapsed_time(b) / reps], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item()
+    rec = {"workload": "MaxSim in-batch-negatives loss, forward + backward: %d ranks x (8 queries x 16 documents), "
+                       "Nq=832, Nd=512 ragged, d=128 (bsz %d)" % (world, 8 * world),
+           "local_negatives_ms": timed(False), "unit": "ms per step, max over ranks"}
+    if world > 1:
+        rec["cross_rank_negatives_ms"] = timed(True)
+        rec["cross_rank_matrix"] = "[8, %d] per rank" % (B * nway * world)
+    return rec
 
 
 def c2_record(args, dev, peaks):
@@ -764,6 +817,35 @@ def c2_record(args, dev, peaks):
                         "scan_ms_per_step": scan_ms_step, "scan_share_of_step": scan_ms_step / ms_step,
                         "algorithmic_flops_per_step": flops_step,
                         "hbm_gbs": (cnt.value // steps) * n_tok * 256.0 / (scan_ms_step * 1e-3) / 1e9}}
+    # ---- C5-shaped record on the same corpus: the retrieval block of the RAG loop (rag_model_blip.py:388-443) for a
+    # batch of 8 questions — exhaustive search of max(5, n_docs) passages, gather of their embeddings out of HBM,
+    # differentiable re-score (block-diagonal launch), backward to the query embeddings
+    try:
+        Qr = Q[:8].float().requires_grad_(True)
+
+        def rag_step():
+            Qr.grad = None
+            out = searcher.retrieve_and_rescore(Qr, 5)
+            out["doc_scores"].sum().backward()
+            return out
+        for _ in range(3):
+            out = rag_step()
+        torch.cuda.synchronize(dev)
+        e0.record()
+        for _ in range(steps):
+            out = rag_step()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms_rag = e0.elapsed_time(e1) / steps
+        ids = out["retrieved_doc_ids"]
+        rec["c5_rag_retrieval_block"] = {
+            "workload": "8 questions x Nq=832: search top-5 over the %d passages, gather, differentiable re-score, "
+                        "backward to the queries (RagModelForBlip.main_retrieve's retrieval block)" % n,
+            "ms_per_step": ms_rag, "questions_per_s": 8e3 / ms_rag,
+            "top1_is_planted_positive": sum(int(ids[b][0] == targets[b]) for b in range(8)) / 8,
+            "query_grad_finite": bool(torch.isfinite(Qr.grad).all())}
+    except Exception as e:
+        rec["c5_rag_retrieval_block"] = {"kind": "error", "sample": repr(e)}
     corpus.close()
     return rec
 
