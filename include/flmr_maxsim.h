@@ -300,8 +300,10 @@ int flmr_debug_maxsim_scores_simt(const flmr_corpus_t* corpus, const void* d_q, 
 
 /* Test infrastructure: which scan kernel searches on the calling thread launch — 0 = chosen per pass (the product
  * behaviour: three epilogue warpgroups for passes with three resident query tiles, two otherwise),
- * 2 = flmr_scan_kernel (two epilogue warpgroups), 3 = flmr_scan3_kernel (three, static query-tile assignment) —
- * so the parity suite can run against either at any shape. */
+ * 2 = flmr_scan_kernel (two epilogue warpgroups), 3 = flmr_scan3_kernel (three, static query-tile assignment),
+ * 4 = the CTA-pair experiment (clusters of two CTAs stream one token range, each D tile fetched once and
+ * TMA-multicast to both; calls it does not fit — odd query counts, row-sliced queries — take the normal path) —
+ * so the parity suite can run against any of them at any shape. */
 int flmr_debug_set_scan_variant(int variant);
 
 /* Test infrastructure: which kernel flmr_maxsim_argmax(_grouped) runs on the calling thread — 0 = chosen by size

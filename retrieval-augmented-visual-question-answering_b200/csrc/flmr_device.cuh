@@ -134,6 +134,29 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst_smem, const CUtensorMap
       : "memory");
 }
 
+// Same, delivered to the same shared-memory offset (and signalled on the same barrier offset) of EVERY CTA of the
+// cluster whose bit is set in `cta_mask`.
+__device__ __forceinline__ void tma_load_2d_multicast(uint32_t dst_smem, const CUtensorMap* map, uint32_t bar,
+                                                      int32_t c0, int32_t c1, uint16_t cta_mask, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster.L2::cache_hint"
+      " [%0], [%1, {%3, %4}], [%2], %5, %6;"
+      ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "h"(cta_mask),
+      "l"(policy)
+      : "memory");
+}
+
+// ---- thread-block cluster ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {   // every thread of every CTA of the cluster
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 // ---- tcgen05 / TMEM -------------------------------------------------------------------------------
 template <uint32_t kCols>
 __device__ __forceinline__ void tmem_alloc(uint32_t smem_dst) {
@@ -158,6 +181,13 @@ __device__ __forceinline__ void tc_fence_after_sync() {
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
                    bar)
+               : "memory");
+}
+
+// tcgen05.commit that arrives on the barrier at the same offset in every CTA of `cta_mask`.
+__device__ __forceinline__ void tc_commit_multicast(uint32_t bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(cta_mask)
                : "memory");
 }
 

@@ -519,6 +519,15 @@ struct flmr_corpus {
   uint32_t* d_tile_end_mask = nullptr; // [n_tiles]
   int32_t* d_tile_first_pid = nullptr; // [n_tiles]
   CUtensorMap tmap_d;
+  // CTA-pair experiment (flmr_debug_set_scan_variant(4)): n_pairs contiguous ranges, one per pair of CTAs, and a
+  // tensor map with a half-tile box
+  int n_pairs = 0;
+  int64_t n_tiles_pair = 0;
+  int32_t* d_pair_row_begin = nullptr;
+  int64_t* d_pair_tile_base = nullptr;
+  uint32_t* d_pair_end_mask = nullptr;
+  int32_t* d_pair_first_pid = nullptr;
+  CUtensorMap tmap_half;
 };
 
 // Streaming corpus construction (index load): the padded token matrix is allocated once, packed rows arrive in
@@ -814,6 +823,80 @@ int ensure_acc(flmr_workspace* ws, int64_t floats) {
   return FLMR_OK;
 }
 
+// CTA-pair experiment (scan variant 4): whole queries only (nq <= 640 rows), an even number of queries per pass, half
+// of them resident in each CTA of a pair; everything else as run_search.  Returns -1 if the call does not fit the
+// experiment (the caller then takes the normal path).
+int run_search_pair(const flmr_corpus* c, flmr_workspace* ws, const void* d_q, int n_queries, int nq, ScanParams p,
+                    int k, float* d_all_scores, float* d_topk_scores, int64_t* d_topk_pids, cudaStream_t st) {
+  const int rbq = (nq + 31) / 32;
+  if (c->n_pairs < 1 || rbq > kRbMax || n_queries < 2 || (n_queries & 1)) return -1;
+  const int h_max = std::min(kNqMax, kRbMax / rbq);            // queries per CTA
+  if (n_queries > ws->max_queries) return -1;
+  const int n_passes = (n_queries + 2 * h_max - 1) / (2 * h_max);
+  int qpp = (n_queries + n_passes - 1) / n_passes;
+  qpp += qpp & 1;
+  if (qpp / 2 > h_max || n_queries % qpp != 0 || n_passes * 2 > kStageMaxPasses) return -1;
+  const int h = qpp / 2;
+  StageParams sp{};
+  for (int i = 0; i < 2 * n_passes; ++i) sp.pass[i] = {i * h, h, 0, nq, rbq, (h * rbq * 32 + kTileM - 1) / kTileM * kTileM};
+  {
+    const int threads = 256;
+    dim3 grid((kMtMax * kTileM * 16 + threads - 1) / threads, static_cast<unsigned>(2 * n_passes));
+    flmr_stage_queries_kernel<<<grid, threads, 0, st>>>(reinterpret_cast<const uint4*>(d_q),
+                                                        reinterpret_cast<uint4*>(ws->d_qpad), nq, sp);
+    FLMR_CUDA(cudaGetLastError());
+    ++g_launches;
+  }
+  p.cta_row_begin = c->d_pair_row_begin;
+  p.cta_tile_base = c->d_pair_tile_base;
+  p.tile_end_mask = c->d_pair_end_mask;
+  p.tile_first_pid = c->d_pair_first_pid;
+  p.cand_q_stride = n_queries;
+  p.n_mtiles = (h * rbq * 32 + kTileM - 1) / kTileM;
+  p.nq_pass = h;
+  p.rbq = rbq;
+  p.acc_in = nullptr;
+  p.k = k;
+  for (int i = 0; i < n_passes; ++i) {
+    p.q_pad = reinterpret_cast<const uint4*>(ws->d_qpad) + static_cast<int64_t>(2 * i) * (kMtMax * kTileM * 16);
+    p.acc_out = d_all_scores ? d_all_scores + static_cast<int64_t>(i) * qpp * c->n_passages : nullptr;
+    p.cand_q_first = i * qpp;
+    EventPair ev{};
+    if (g_profiling) {
+      FLMR_CUDA(cudaEventCreate(&ev.a));
+      FLMR_CUDA(cudaEventCreate(&ev.b));
+      FLMR_CUDA(cudaEventRecord(ev.a, st));
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(static_cast<unsigned>(2 * c->n_pairs));
+    cfg.blockDim = dim3(kScanThreads);
+    cfg.dynamicSmemBytes = ScanSmem::kBytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    FLMR_CUDA(cudaLaunchKernelEx(&cfg, flmr_scan_kernel<false, true>, c->tmap_half, p));
+    ++g_launches;
+    if (g_profiling) {
+      FLMR_CUDA(cudaEventRecord(ev.b, st));
+      g_scan_events.push_back(ev);
+    }
+  }
+  if (k > 0) {
+    if (static_cast<int64_t>(c->n_pairs) * k > kMergeThreads * kMergePer)
+      return fail(FLMR_ERR_UNSUPPORTED, "n_pairs*k exceeds merge capacity");
+    flmr_merge_kernel<<<n_queries, kMergeThreads, 0, st>>>(ws->d_cand_keys, nullptr, nullptr, c->n_pairs, n_queries, k,
+                                                           k, c->pid_base, d_topk_scores, d_topk_pids);
+    FLMR_CUDA(cudaGetLastError());
+    ++g_launches;
+  }
+  return FLMR_OK;
+}
+
 // Shared driver of flmr_maxsim_scores / flmr_maxsim_topk.
 int run_search(const flmr_corpus* c, flmr_workspace* ws, const void* d_q, int n_queries, int nq,
                unsigned flags, int k, float* d_all_scores, float* d_topk_scores,
@@ -865,6 +948,10 @@ int run_search(const flmr_corpus* c, flmr_workspace* ws, const void* d_q, int n_
   }
 #endif
 
+  if (g_scan_variant == 4) {   // CTA-pair experiment, when the call fits it
+    const int prc = run_search_pair(c, ws, d_q, n_queries, nq, p, k, d_all_scores, d_topk_scores, d_topk_pids, st);
+    if (prc >= 0) return prc;
+  }
   // a call is processed in chunks of at most ws->max_queries queries (the candidate buffer's capacity);
   // within a chunk: every pass's scan, then ONE merge launch over all of the chunk's queries
   std::vector<PassPlan> plan;
@@ -943,6 +1030,22 @@ int finish_corpus(flmr_corpus* c, const std::vector<int64_t>& poff, const int32_
   }
   if ((rc = encode_rows_map(&c->tmap_d, c->d_tokens, static_cast<uint64_t>(n_rows), kTileN)))
     return bail(rc);
+  if (n_ctas >= 2 && n_passages >= n_ctas / 2) {   // CTA-pair experiment: its own partition + half-tile tensor map
+    std::vector<int32_t> row_begin, first_pid;
+    std::vector<int64_t> tile_base;
+    std::vector<uint32_t> end_mask;
+    c->n_pairs = n_ctas / 2;
+    build_partition(poff, c->n_pairs, kTileN, &row_begin, &tile_base, &end_mask, &first_pid);
+    c->n_tiles_pair = static_cast<int64_t>(end_mask.size());
+    if ((rc = dev_upload(&c->d_pair_row_begin, row_begin, &c->hbm_bytes))) return bail(rc);
+    if ((rc = dev_upload(&c->d_pair_tile_base, tile_base, &c->hbm_bytes))) return bail(rc);
+    if ((rc = dev_upload(&c->d_pair_end_mask, end_mask, &c->hbm_bytes))) return bail(rc);
+    if ((rc = dev_upload(&c->d_pair_first_pid, first_pid, &c->hbm_bytes))) return bail(rc);
+    if ((rc = encode_rows_map(&c->tmap_half, c->d_tokens, static_cast<uint64_t>(n_rows), kTileN / 2))) return bail(rc);
+    cudaError_t e3 = cudaFuncSetAttribute(flmr_scan_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          ScanSmem::kBytes);
+    if (e3 != cudaSuccess) return bail(fail(FLMR_ERR_CUDA, "pair kernel attribute: %s", cudaGetErrorString(e3)));
+  }
   {  // per-device function attribute, set here (idempotent) rather than at launch time
     cudaError_t e1 = cudaFuncSetAttribute(flmr_scan_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           ScanSmem::kBytes);
@@ -1104,6 +1207,10 @@ int flmr_corpus_destroy(flmr_corpus_t* c) {
   cudaFree(c->d_cta_tile_base);
   cudaFree(c->d_tile_end_mask);
   cudaFree(c->d_tile_first_pid);
+  cudaFree(c->d_pair_row_begin);
+  cudaFree(c->d_pair_tile_base);
+  cudaFree(c->d_pair_end_mask);
+  cudaFree(c->d_pair_first_pid);
   delete c;
   return FLMR_OK;
 }
@@ -1724,8 +1831,8 @@ int flmr_debug_maxsim_scores_simt(const flmr_corpus_t* c, const void* d_q, int n
 }
 
 int flmr_debug_set_scan_variant(int variant) {
-  if (variant != 0 && variant != 2 && variant != 3)
-    return fail(FLMR_ERR_INVALID_ARG, "variant must be 0 (default), 2 or 3 (epilogue warpgroups)");
+  if (variant != 0 && variant != 2 && variant != 3 && variant != 4)
+    return fail(FLMR_ERR_INVALID_ARG, "variant must be 0 (default), 2 or 3 (epilogue warpgroups) or 4 (CTA-pair experiment)");
   g_scan_variant = variant;
   return FLMR_OK;
 }

@@ -258,7 +258,14 @@ __device__ __noinline__ void topk_replace_min(uint64_t* keys, int k, uint64_t ca
 // ---- the kernel -------------------------------------------------------------------------------
 // kDebug = false is the product instantiation: no timing-experiment branches, no timestamps in the
 // hot loops (the epilogue is bound by instruction issue slots, every instruction there counts).
-template <bool kDebug>
+//
+// kPair = true is the CTA-PAIR EXPERIMENT (launched as clusters of two CTAs): both CTAs of a pair stream the SAME
+// token range, each with its own resident queries (twice the queries per corpus pass); every D tile is fetched from
+// L2 / HBM once — CTA r loads rows [48 r, 48 r + 48) of the tile and TMA-multicasts them into both CTAs' shared
+// memory — and a D stage is recycled when the issuers of BOTH CTAs have committed it (multicast tcgen05.commit).
+// The MMAs stay cta_group::1: this isolates what a pair can save (half the HBM / L2 traffic per query) from what it
+// cannot (the accumulator drain), see DESIGN.md 4.1.
+template <bool kDebug, bool kPair = false>
 __global__ void __launch_bounds__(kScanThreads, 1)
 flmr_scan_kernel(const __grid_constant__ CUtensorMap tmap_d, const ScanParams p) {
   const int dbg = kDebug ? p.debug_mode : 0;
@@ -270,7 +277,8 @@ flmr_scan_kernel(const __grid_constant__ CUtensorMap tmap_d, const ScanParams p)
   const uint32_t smem_base = smem_u32(smem);
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int cta = blockIdx.x;
+  const int cta = kPair ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);   // partition / list index
+  const uint32_t pair_rank = kPair ? cluster_ctarank() : 0u;
 
   const uint32_t bar_base = smem_base + S::kOffBars;
   const uint32_t bar_q_full = bar_base;
@@ -302,7 +310,7 @@ flmr_scan_kernel(const __grid_constant__ CUtensorMap tmap_d, const ScanParams p)
     mbar_init(bar_q_full, 4);        // one arrive per query-staging warp
     for (int s = 0; s < kDStages; ++s) {
       mbar_init(bar_d_full(s), 1);
-      mbar_init(bar_d_empty(s), kMmaWarps);
+      mbar_init(bar_d_empty(s), kPair ? 2 * kMmaWarps : kMmaWarps);   // pair: the issuers of both CTAs
     }
     for (int s = 0; s < kMaxAccStages; ++s) {
       mbar_init(bar_t_full(s), 1);
@@ -334,6 +342,7 @@ flmr_scan_kernel(const __grid_constant__ CUtensorMap tmap_d, const ScanParams p)
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
+  if constexpr (kPair) cluster_sync_all();   // the peer's barriers exist before anything is multicast to them
   const uint32_t tmem_base = *tmem_ptr_smem;
 
   if (warp == kWarpProducer) {
@@ -345,11 +354,18 @@ flmr_scan_kernel(const __grid_constant__ CUtensorMap tmap_d, const ScanParams p)
       const uint32_t ph = (t / kDStages) & 1;
       mbar_wait(bar_d_empty(s), ph ^ 1u, p.status, kDevTimeoutProducer);
       if (elect_one_sync()) {
-        mbar_arrive_expect_tx(bar_d_full(s), kDTileBytes);
+        mbar_arrive_expect_tx(bar_d_full(s), kDTileBytes);   // (pair: 12 KB from this CTA's loads + 12 KB from the peer's)
         const uint32_t dst = smem_base + S::kOffD + s * kDTileBytes;
         const int32_t row = row_begin + t * kTileN;
-        tma_load_2d(dst, &tmap_d, bar_d_full(s), 0, row, kPolicyEvictFirst);
-        tma_load_2d(dst + kDKBlockBytes, &tmap_d, bar_d_full(s), 64, row, kPolicyEvictFirst);
+        if constexpr (kPair) {   // tmap_d has a (kTileN / 2)-row box here
+          const uint32_t half = pair_rank * (kTileN / 2);
+          tma_load_2d_multicast(dst + half * 128, &tmap_d, bar_d_full(s), 0, row + half, 3, kPolicyEvictFirst);
+          tma_load_2d_multicast(dst + kDKBlockBytes + half * 128, &tmap_d, bar_d_full(s), 64, row + half, 3,
+                                kPolicyEvictFirst);
+        } else {
+          tma_load_2d(dst, &tmap_d, bar_d_full(s), 0, row, kPolicyEvictFirst);
+          tma_load_2d(dst + kDKBlockBytes, &tmap_d, bar_d_full(s), 64, row, kPolicyEvictFirst);
+        }
       }
       __syncwarp();
     }
@@ -402,7 +418,10 @@ flmr_scan_kernel(const __grid_constant__ CUtensorMap tmap_d, const ScanParams p)
         __syncwarp();
       }
       // this issuer's MMAs on the D stage are complete -> producer (both issuers must arrive)
-      if (elect_one_sync()) tc_commit(bar_d_empty(s));
+      if (elect_one_sync()) {
+        if constexpr (kPair) tc_commit_multicast(bar_d_empty(s), 3);
+        else tc_commit(bar_d_empty(s));
+      }
       __syncwarp();
     }
   } else if (warp < kEpiWarps) {
@@ -428,7 +447,8 @@ flmr_scan_kernel(const __grid_constant__ CUtensorMap tmap_d, const ScanParams p)
     // bf16 pair (k = 2c, 2c+1), i.e. the row's 256 bytes verbatim.
     if (wg == 0) {
       for (int mt = 0; mt < n_mtiles; ++mt) {
-        const uint4* src = p.q_pad + (static_cast<int64_t>(mt) * kTileM + quad * 32 + lane) * 16;
+        const uint4* src = p.q_pad + (static_cast<int64_t>(pair_rank) * (kMtMax * kTileM) +   // pair: CTA r's staging slot
+                                      static_cast<int64_t>(mt) * kTileM + quad * 32 + lane) * 16;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           uint32_t w[32];
@@ -524,6 +544,7 @@ flmr_scan_kernel(const __grid_constant__ CUtensorMap tmap_d, const ScanParams p)
     // Per D tile and per (query, passage ending in the tile): sum the row-block partials in fixed
     // order (deterministic), add/store partial scores if requested, offer to the top-k list.
     const int rw = warp - kWarpRed0;  // reducer 0..kRedWarps-1 owns queries b = rw (mod kRedWarps)
+    const int q_off = static_cast<int>(pair_rank) * p.nq_pass;   // pair: CTA r's queries follow CTA 0's in every per-query array
     const float* partial = reinterpret_cast<const float*>(smem + S::kOffPartial);
     uint64_t* keys = reinterpret_cast<uint64_t*>(smem + S::kOffKeys);
     uint64_t* minkey_s = reinterpret_cast<uint64_t*>(smem + S::kOffMinKey);
@@ -565,7 +586,7 @@ flmr_scan_kernel(const __grid_constant__ CUtensorMap tmap_d, const ScanParams p)
 #pragma unroll 8
                 for (int j = 0; j < 32; ++j) sc += lp[r * kLaneStride + j];
               }
-              const int64_t gi = static_cast<int64_t>(b) * p.n_passages + pid;
+              const int64_t gi = static_cast<int64_t>(q_off + b) * p.n_passages + pid;
               if (p.acc_in) sc += __ldg(p.acc_in + gi);
               if (p.acc_out) p.acc_out[gi] = sc;
               key = (static_cast<uint64_t>(float_to_ordered(sc)) << 32) |
@@ -606,7 +627,7 @@ flmr_scan_kernel(const __grid_constant__ CUtensorMap tmap_d, const ScanParams p)
 #pragma unroll 2
               for (int r = 0; r < p.rbq; ++r) sc += pr[r * kSlots];
             }
-            const int64_t gi = static_cast<int64_t>(b) * p.n_passages + pid;
+            const int64_t gi = static_cast<int64_t>(q_off + b) * p.n_passages + pid;
             if (p.acc_in) sc += __ldg(p.acc_in + gi);
             if (p.acc_out && lane == 0) p.acc_out[gi] = sc;
             if (p.k > 0) {
@@ -633,7 +654,7 @@ flmr_scan_kernel(const __grid_constant__ CUtensorMap tmap_d, const ScanParams p)
     if (p.k > 0) {
       __syncwarp();
       for (int b = rw; b < p.nq_pass; b += kRedWarps) {
-        uint64_t* dst = p.cand_keys + (static_cast<int64_t>(cta) * p.cand_q_stride + p.cand_q_first + b) * p.k;
+        uint64_t* dst = p.cand_keys + (static_cast<int64_t>(cta) * p.cand_q_stride + p.cand_q_first + q_off + b) * p.k;
         for (int i = lane; i < p.k; i += 32) dst[i] = keys[b * kMaxK + i];
       }
     }
@@ -641,6 +662,7 @@ flmr_scan_kernel(const __grid_constant__ CUtensorMap tmap_d, const ScanParams p)
 
   // ---- teardown -----------------------------------------------------------------------------------
   __syncthreads();
+  if constexpr (kPair) cluster_sync_all();   // no CTA leaves while its peer may still signal its barriers
   if (warp == kWarpMma) {
     tc_fence_after_sync();
     tmem_dealloc<512>(tmem_base);

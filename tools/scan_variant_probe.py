@@ -21,6 +21,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--passages", type=int, default=200_000)
     ap.add_argument("--skip-parity", action="store_true")
+    ap.add_argument("--sustained", type=float, default=0.0, help="seconds per block of the power-capped A/B (0 = skip)")
     args = ap.parse_args()
     L = _cabi.lib()
     dev = torch.device("cuda", 0)
@@ -37,11 +38,13 @@ def main():
             L.flmr_debug_set_scan_variant(2)
             s2 = R.maxsim_scores(corpus, Qt, relu=relu)
             t2 = R.maxsim_topk(corpus, Qt, min(k, n), relu=relu)
-            L.flmr_debug_set_scan_variant(3)
-            s3 = R.maxsim_scores(corpus, Qt, relu=relu)
-            t3 = R.maxsim_topk(corpus, Qt, min(k, n), relu=relu)
-            torch.cuda.synchronize()
-            ok = torch.equal(s2, s3) and torch.equal(t2[0], t3[0]) and torch.equal(t2[1], t3[1])
+            ok = True
+            for variant in (3, 4):
+                L.flmr_debug_set_scan_variant(variant)
+                s3 = R.maxsim_scores(corpus, Qt, relu=relu)
+                t3 = R.maxsim_topk(corpus, Qt, min(k, n), relu=relu)
+                torch.cuda.synchronize()
+                ok = ok and torch.equal(s2, s3) and torch.equal(t2[0], t3[0]) and torch.equal(t2[1], t3[1])
             ref = O.maxsim_scores(Q, D, dl, relu=relu)
             rel = float(np.max(np.abs(s3.cpu().numpy() - ref) / np.maximum(np.abs(ref), 1e-6)))
             print("n=%d nd=%d B=%d nq=%d ragged=%s relu=%s k=%d: identical=%s max_rel_vs_oracle=%.1e"
@@ -59,7 +62,9 @@ def main():
     print("| shape | variant | scan launch ms | TFLOP/s (algorithmic) | GB/s | q/s at 1M |\n|---|---|---:|---:|---:|---:|")
     for (B, nq) in [(16, 320), (2, 320), (1, 320), (20, 32), (1, 32), (3, 832), (4, 256), (2, 128)]:
         Q = torch.nn.functional.normalize(torch.randn((B, nq, 128), device=dev, generator=g), dim=-1).bfloat16()
-        for variant in (2, 3):
+        for variant in (2, 3, 4):
+            if variant == 4 and (B % 2 or nq > 640):
+                continue
             L.flmr_debug_set_scan_variant(variant)
             for _ in range(2):
                 R.maxsim_topk(corpus, Q, 5)
@@ -79,9 +84,31 @@ def main():
             ms_call = e0.elapsed_time(e1) / iters
             ms_launch = tot.value / cnt.value
             flops_call = 2.0 * B * nq * 128 * n_p * nd
-            print("| B=%d Nq=%d | %d WGs | %.3f | %.0f | %.0f | %.1f |"
-                  % (B, nq, variant, ms_launch, flops_call / (tot.value / iters) / 1e9,
+            print("| B=%d Nq=%d | %s | %.3f | %.0f | %.0f | %.1f |"
+                  % (B, nq, {2: "2 WGs", 3: "3 WGs", 4: "CTA pairs (multicast)"}[variant], ms_launch, flops_call / (tot.value / iters) / 1e9,
                      n_p * nd * 256.0 / ms_launch / 1e6, B / ms_call * 1e3 * n_p / 1e6), flush=True)
+    # sustained (power-capped) A/B at the headline shape: alternate the two variants in blocks of ~2 s, three rounds
+    if args.sustained:
+        import time
+        Q = torch.nn.functional.normalize(torch.randn((16, 320, 128), device=dev, generator=g), dim=-1).bfloat16()
+        flops_call = 2.0 * 16 * 320 * 128 * n_p * nd
+        print("\n| sustained block | variant | TFLOP/s |\n|---|---|---:|")
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for rnd in range(3):
+            for variant in (2, 4):
+                L.flmr_debug_set_scan_variant(variant)
+                R.maxsim_topk(corpus, Q, 5)
+                torch.cuda.synchronize()
+                t_end, calls = time.time() + args.sustained, 0
+                e0.record()
+                while time.time() < t_end:
+                    for _ in range(4):
+                        R.maxsim_topk(corpus, Q, 5)
+                    calls += 4
+                    e1.record()
+                    e1.synchronize()
+                print("| %d | %s | %.0f |" % (rnd, {2: "2 WGs", 4: "CTA pairs (multicast)"}[variant],
+                                            flops_call * calls / (e0.elapsed_time(e1) * 1e-3) / 1e12), flush=True)
     L.flmr_debug_set_scan_variant(0)
 
 
