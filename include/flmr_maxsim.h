@@ -298,11 +298,12 @@ int flmr_maxsim_backward_grouped(const void* d_q, int n_queries, int nq, const v
 int flmr_debug_maxsim_scores_simt(const flmr_corpus_t* corpus, const void* d_q, int n_queries,
                                   int nq, unsigned flags, float* d_out_scores, void* stream);
 
-/* Test infrastructure: which scan kernel searches on the calling thread launch — 0 = chosen per pass (the product
- * behaviour: three epilogue warpgroups for passes with three resident query tiles, two otherwise),
- * 2 = flmr_scan_kernel (two epilogue warpgroups), 3 = flmr_scan3_kernel (three, static query-tile assignment),
- * 4 = the CTA-pair experiment (clusters of two CTAs stream one token range, each D tile fetched once and
- * TMA-multicast to both; calls it does not fit — odd query counts, row-sliced queries — take the normal path) —
+/* Test infrastructure: which scan kernel searches on the calling thread launch — 0 = chosen per call and pass (the
+ * product behaviour: CTA-pair passes for as many queries as fill them when the shard spans every SM, else normal
+ * passes, those with three resident query tiles on the three-warpgroup kernel),
+ * 2 = flmr_scan_kernel (two epilogue warpgroups), normal passes only, 3 = flmr_scan3_kernel (three warpgroups,
+ * static query-tile assignment), normal passes only, 4 = CTA-pair passes (clusters of two CTAs stream one token
+ * range, each D tile fetched once and TMA-multicast to both) whenever a call has enough queries, on any shard —
  * so the parity suite can run against any of them at any shape. */
 int flmr_debug_set_scan_variant(int variant);
 

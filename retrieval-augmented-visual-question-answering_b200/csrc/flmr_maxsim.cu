@@ -522,6 +522,7 @@ struct flmr_corpus {
   // CTA-pair experiment (flmr_debug_set_scan_variant(4)): n_pairs contiguous ranges, one per pair of CTAs, and a
   // tensor map with a half-tile box
   int n_pairs = 0;
+  int sm_count = 0;
   int64_t n_tiles_pair = 0;
   int32_t* d_pair_row_begin = nullptr;
   int64_t* d_pair_tile_base = nullptr;
@@ -823,20 +824,26 @@ int ensure_acc(flmr_workspace* ws, int64_t floats) {
   return FLMR_OK;
 }
 
-// CTA-pair experiment (scan variant 4): whole queries only (nq <= 640 rows), an even number of queries per pass, half
-// of them resident in each CTA of a pair; everything else as run_search.  Returns -1 if the call does not fit the
-// experiment (the caller then takes the normal path).
+// CTA-pair passes: clusters of two CTAs stream one token range, each CTA with its own resident queries, every D tile
+// fetched from L2 / HBM once and TMA-multicast into both (flmr_scan_kernel<false, true>).  Each CTA keeps exactly the
+// residency a normal pass would give it (qpp_n queries, at least four 128-row tiles), so a pair pass serves
+// 2 * qpp_n queries per corpus pass: half the HBM / L2 traffic per query, and on this power-capped part ~6 % more
+// sustained throughput at the headline shape (profiles/r02_scan_variant_probe.md).  Handles the largest prefix of the
+// call that fills whole pair passes and returns its length in *handled (0: the call does not qualify); the caller
+// runs the remaining queries through normal passes.
 int run_search_pair(const flmr_corpus* c, flmr_workspace* ws, const void* d_q, int n_queries, int nq, ScanParams p,
-                    int k, float* d_all_scores, float* d_topk_scores, int64_t* d_topk_pids, cudaStream_t st) {
+                    int k, float* d_all_scores, float* d_topk_scores, int64_t* d_topk_pids, cudaStream_t st,
+                    int* handled) {
+  *handled = 0;
   const int rbq = (nq + 31) / 32;
-  if (c->n_pairs < 1 || rbq > kRbMax || n_queries < 2 || (n_queries & 1)) return -1;
-  const int h_max = std::min(kNqMax, kRbMax / rbq);            // queries per CTA
-  if (n_queries > ws->max_queries) return -1;
-  const int n_passes = (n_queries + 2 * h_max - 1) / (2 * h_max);
-  int qpp = (n_queries + n_passes - 1) / n_passes;
-  qpp += qpp & 1;
-  if (qpp / 2 > h_max || n_queries % qpp != 0 || n_passes * 2 > kStageMaxPasses) return -1;
-  const int h = qpp / 2;
+  if (c->n_pairs < 1 || rbq > kRbMax) return FLMR_OK;
+  const int h = std::min(kNqMax, kRbMax / rbq);               // queries per CTA = a normal pass's residency
+  if (h * rbq * 32 < 4 * kTileM) return FLMR_OK;               // fewer than four tiles per CTA: pairs measured slower
+  const int qpp = 2 * h;
+  int n_passes = std::min(n_queries, ws->max_queries) / qpp;
+  n_passes = std::min(n_passes, kStageMaxPasses / 2);
+  if (n_passes < 1) return FLMR_OK;
+  const int nq_handled = n_passes * qpp;
   StageParams sp{};
   for (int i = 0; i < 2 * n_passes; ++i) sp.pass[i] = {i * h, h, 0, nq, rbq, (h * rbq * 32 + kTileM - 1) / kTileM * kTileM};
   {
@@ -851,7 +858,7 @@ int run_search_pair(const flmr_corpus* c, flmr_workspace* ws, const void* d_q, i
   p.cta_tile_base = c->d_pair_tile_base;
   p.tile_end_mask = c->d_pair_end_mask;
   p.tile_first_pid = c->d_pair_first_pid;
-  p.cand_q_stride = n_queries;
+  p.cand_q_stride = nq_handled;
   p.n_mtiles = (h * rbq * 32 + kTileM - 1) / kTileM;
   p.nq_pass = h;
   p.rbq = rbq;
@@ -889,11 +896,12 @@ int run_search_pair(const flmr_corpus* c, flmr_workspace* ws, const void* d_q, i
   if (k > 0) {
     if (static_cast<int64_t>(c->n_pairs) * k > kMergeThreads * kMergePer)
       return fail(FLMR_ERR_UNSUPPORTED, "n_pairs*k exceeds merge capacity");
-    flmr_merge_kernel<<<n_queries, kMergeThreads, 0, st>>>(ws->d_cand_keys, nullptr, nullptr, c->n_pairs, n_queries, k,
-                                                           k, c->pid_base, d_topk_scores, d_topk_pids);
+    flmr_merge_kernel<<<nq_handled, kMergeThreads, 0, st>>>(ws->d_cand_keys, nullptr, nullptr, c->n_pairs, nq_handled,
+                                                            k, k, c->pid_base, d_topk_scores, d_topk_pids);
     FLMR_CUDA(cudaGetLastError());
     ++g_launches;
   }
+  *handled = nq_handled;
   return FLMR_OK;
 }
 
@@ -948,9 +956,21 @@ int run_search(const flmr_corpus* c, flmr_workspace* ws, const void* d_q, int n_
   }
 #endif
 
-  if (g_scan_variant == 4) {   // CTA-pair experiment, when the call fits it
-    const int prc = run_search_pair(c, ws, d_q, n_queries, nq, p, k, d_all_scores, d_topk_scores, d_topk_pids, st);
-    if (prc >= 0) return prc;
+  // CTA-pair passes for as many queries as fill whole pair passes (variant 0 = product: whenever the shard spans
+  // every SM; 4 = always when possible; 2 / 3 = never), normal passes for the rest
+  if (g_scan_variant == 4 || (g_scan_variant == 0 && c->n_pairs * 2 == c->sm_count)) {
+    int handled = 0;
+    if (int prc = run_search_pair(c, ws, d_q, n_queries, nq, p, k, d_all_scores, d_topk_scores, d_topk_pids, st,
+                                  &handled))
+      return prc;
+    if (handled > 0) {
+      if (handled == n_queries) return FLMR_OK;
+      d_q = static_cast<const __nv_bfloat16*>(d_q) + static_cast<int64_t>(handled) * nq * kDim;
+      if (d_all_scores) d_all_scores += static_cast<int64_t>(handled) * c->n_passages;
+      if (d_topk_scores) d_topk_scores += static_cast<int64_t>(handled) * k;
+      if (d_topk_pids) d_topk_pids += static_cast<int64_t>(handled) * k;
+      n_queries -= handled;
+    }
   }
   // a call is processed in chunks of at most ws->max_queries queries (the candidate buffer's capacity);
   // within a chunk: every pass's scan, then ONE merge launch over all of the chunk's queries
@@ -1035,6 +1055,7 @@ int finish_corpus(flmr_corpus* c, const std::vector<int64_t>& poff, const int32_
     std::vector<int64_t> tile_base;
     std::vector<uint32_t> end_mask;
     c->n_pairs = n_ctas / 2;
+    c->sm_count = sm_count;
     build_partition(poff, c->n_pairs, kTileN, &row_begin, &tile_base, &end_mask, &first_pid);
     c->n_tiles_pair = static_cast<int64_t>(end_mask.size());
     if ((rc = dev_upload(&c->d_pair_row_begin, row_begin, &c->hbm_bytes))) return bail(rc);

@@ -296,7 +296,7 @@ def test_three_warpgroup_scan_kernel_is_bit_identical(case):
     Qt = torch.from_numpy(Q)
     try:
         outs = {}
-        for variant in (2, 3, 0):
+        for variant in (2, 3, 0, 4):
             _cabi.check(L.flmr_debug_set_scan_variant(variant))
             outs[variant] = (R.maxsim_scores(corpus, Qt, relu=relu), *R.maxsim_topk(corpus, Qt, min(k, n), relu=relu))
     finally:
@@ -304,6 +304,12 @@ def test_three_warpgroup_scan_kernel_is_bit_identical(case):
     for variant in (3, 0):
         for x, y in zip(outs[2], outs[variant]):
             assert torch.equal(x, y)
+    # CTA-pair passes (variant 4; the product uses them on shards that span every SM): another partition of the
+    # passages, so a passage that is the 5th or later to end inside its tile is summed lanes-first instead of
+    # row-blocks-first — last-bit differences in the scores, the same ranking
+    np.testing.assert_allclose(outs[4][0].cpu().numpy(), outs[2][0].cpu().numpy(), rtol=2e-6)
+    assert torch.equal(outs[4][2], outs[2][2])
+    np.testing.assert_allclose(outs[4][1].cpu().numpy(), outs[2][1].cpu().numpy(), rtol=2e-6)
     ref = O.maxsim_scores(Q, D, dl, relu=relu)
     np.testing.assert_allclose(outs[3][0].cpu().numpy(), ref, rtol=2e-5)
 

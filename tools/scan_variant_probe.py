@@ -44,7 +44,11 @@ def main():
                 s3 = R.maxsim_scores(corpus, Qt, relu=relu)
                 t3 = R.maxsim_topk(corpus, Qt, min(k, n), relu=relu)
                 torch.cuda.synchronize()
-                ok = ok and torch.equal(s2, s3) and torch.equal(t2[0], t3[0]) and torch.equal(t2[1], t3[1])
+                if variant == 3:     # same partition, same summation order: bit-identical
+                    ok = ok and torch.equal(s2, s3) and torch.equal(t2[0], t3[0]) and torch.equal(t2[1], t3[1])
+                else:                # the pair partition moves tile boundaries: a passage that is the 5th+ to end
+                    # in its tile is summed lanes-first instead of row-blocks-first -> last-bit differences
+                    ok = ok and torch.allclose(s2, s3, rtol=2e-6, atol=0) and torch.equal(t2[1], t3[1])
             ref = O.maxsim_scores(Q, D, dl, relu=relu)
             rel = float(np.max(np.abs(s3.cpu().numpy() - ref) / np.maximum(np.abs(ref), 1e-6)))
             print("n=%d nd=%d B=%d nq=%d ragged=%s relu=%s k=%d: identical=%s max_rel_vs_oracle=%.1e"
@@ -109,6 +113,23 @@ def main():
                     e1.synchronize()
                 print("| %d | %s | %.0f |" % (rnd, {2: "2 WGs", 4: "CTA pairs (multicast)"}[variant],
                                             flops_call * calls / (e0.elapsed_time(e1) * 1e-3) / 1e12), flush=True)
+        Q1 = Q[:1].contiguous()
+        flops1 = 2.0 * 320 * 128 * n_p * nd
+        print("\n| sustained block, B=1 Nq=320 | variant | TFLOP/s (algorithmic) |\n|---|---|---:|")
+        for rnd in range(3):
+            for variant in (2, 3):
+                L.flmr_debug_set_scan_variant(variant)
+                R.maxsim_topk(corpus, Q1, 5)
+                torch.cuda.synchronize()
+                t_end, calls = time.time() + args.sustained, 0
+                e0.record()
+                while time.time() < t_end:
+                    for _ in range(8):
+                        R.maxsim_topk(corpus, Q1, 5)
+                    calls += 8
+                    e1.record()
+                    e1.synchronize()
+                print("| %d | %d WGs | %.0f |" % (rnd, variant, flops1 * calls / (e0.elapsed_time(e1) * 1e-3) / 1e12), flush=True)
     L.flmr_debug_set_scan_variant(0)
 
 
