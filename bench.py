@@ -629,8 +629,9 @@ def run_ours(args):
         info_tokens = n_tok
         # dominant kernel = flmr_scan_kernel: one launch scans this rank's shard for the queries resident
         # in that pass.  Algorithmic work per launch (DESIGN.md "Roofline"):
-        q_per_launch = max(1, 20 // ((nq + 31) // 32)) if (nq + 31) // 32 <= 20 else 1
-        q_per_launch = min(q_per_launch, B)
+        # queries resident per scan launch, from the launches actually timed (2 per normal pass at Nq = 320; 4 per
+        # CTA-pair pass, where two CTAs stream one token range with two queries each)
+        q_per_launch = B * args.steps / max(r_dev["scan_n"], 1)
         flops_launch = 2.0 * q_per_launch * nq * 128 * info_tokens
         bytes_launch = info_tokens * 256.0
         scan_avg_ms = r_dev["scan_ms"] / max(r_dev["scan_n"], 1)
@@ -645,7 +646,7 @@ def run_ours(args):
             if os.path.exists(tpath) and world == 1 and (n_total, nd, nq) == (1_000_000, 180, 320):
                 with open(tpath) as f:
                     tj = json.load(f)
-                if tj.get("kernel_source_sha") == sha and tj.get("queries_per_launch", 2) == q_per_launch:
+                if tj.get("kernel_source_sha") == sha and abs(tj.get("queries_per_launch", 2) - q_per_launch) < 1e-6:
                     traffic = tj.get("traffic_bytes_per_launch")
                     traffic_src = "profiles/%s (ncu --set full: dram__bytes_read.sum + dram__bytes_write.sum per launch; kernel sources %s)" % (tname, sha)
                     break
