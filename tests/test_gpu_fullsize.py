@@ -54,6 +54,15 @@ def test_full_size_1m_passages_properties():
     rel = ((s_all[:1] - s_simt).abs() / s_simt.abs().clamp_min(1e-6)).max().item()
     assert rel < 2e-5, rel
     assert torch.equal(s_all, R.maxsim_scores(corpus, Q))                    # deterministic
+    # four queries = one CTA-pair pass (the headline's path): same scores as the normal passes above up to the last
+    # bits a different tile partition can move, same ranking, fused top-k == sort of its own scores
+    Q4 = torch.cat([Q, Q[:1].flip(1)])
+    s4 = R.maxsim_scores(corpus, Q4)
+    np.testing.assert_allclose(s4[:3].cpu().numpy(), s_all.cpu().numpy(), rtol=2e-6)
+    ts4, tp4 = R.maxsim_topk(corpus, Q4, 100)
+    rs4, rp4 = torch.sort(s4, dim=1, descending=True, stable=True)
+    assert torch.equal(tp4, rp4[:, :100]) and torch.equal(ts4, rs4[:, :100])
+    assert torch.equal(tp4[:3, :5], tp)
     corpus.close()
 
 

@@ -301,15 +301,15 @@ def test_three_warpgroup_scan_kernel_is_bit_identical(case):
             outs[variant] = (R.maxsim_scores(corpus, Qt, relu=relu), *R.maxsim_topk(corpus, Qt, min(k, n), relu=relu))
     finally:
         L.flmr_debug_set_scan_variant(0)
-    for variant in (3, 0):
-        for x, y in zip(outs[2], outs[variant]):
-            assert torch.equal(x, y)
+    for x, y in zip(outs[2], outs[3]):
+        assert torch.equal(x, y)
     # CTA-pair passes (variant 4; the product uses them on shards that span every SM): another partition of the
     # passages, so a passage that is the 5th or later to end inside its tile is summed lanes-first instead of
     # row-blocks-first — last-bit differences in the scores, the same ranking
-    np.testing.assert_allclose(outs[4][0].cpu().numpy(), outs[2][0].cpu().numpy(), rtol=2e-6)
-    assert torch.equal(outs[4][2], outs[2][2])
-    np.testing.assert_allclose(outs[4][1].cpu().numpy(), outs[2][1].cpu().numpy(), rtol=2e-6)
+    for variant in (4, 0):
+        np.testing.assert_allclose(outs[variant][0].cpu().numpy(), outs[2][0].cpu().numpy(), rtol=2e-6)
+        assert torch.equal(outs[variant][2], outs[2][2])
+        np.testing.assert_allclose(outs[variant][1].cpu().numpy(), outs[2][1].cpu().numpy(), rtol=2e-6)
     ref = O.maxsim_scores(Q, D, dl, relu=relu)
     np.testing.assert_allclose(outs[3][0].cpu().numpy(), ref, rtol=2e-5)
 
@@ -335,3 +335,34 @@ def test_c2_shape_against_the_c_oracle():
     rs, rp = O.topk(ref, k)
     assert np.array_equal(p.cpu().numpy(), rp)
     np.testing.assert_allclose(s.cpu().numpy(), rs, rtol=2e-5)
+
+
+def test_big_cta_pair_passes_properties(R, big):
+    """120k passages, SIX Nq = 320 queries: on a shard that spans every SM the product runs the first four through
+    one CTA-pair pass (clusters of two CTAs, TMA multicast, two queries resident in each CTA) and the last two through
+    a normal pass.  Fused top-k == stable sort of all scores (same call pattern), deterministic, and equal — scores to
+    the last bits a different tile partition can move, ids exactly — to the single-CTA kernel forced onto all six."""
+    from ravqa_b200 import _cabi
+    corpus, D, Q3, n_p, nd = big
+    L = _cabi.lib()
+    g = torch.Generator(device="cuda").manual_seed(9)
+    Q = torch.nn.functional.normalize(torch.randn((6, 320, 128), device="cuda", generator=g), dim=-1).to(torch.bfloat16)
+    for b, t in enumerate([0, 1, n_p // 2, n_p - 1, 77, n_p - 2]):        # planted positives incl. both corpus ends
+        Q[b, :32] = D[t * nd: t * nd + 32]
+    L.flmr_launch_count(1)
+    s_all = R.maxsim_scores(corpus, Q)
+    assert L.flmr_launch_count(1) == 4                                    # (staging + pair pass of 4) + (staging + normal pass of 2)
+    for k in (5, 100):
+        ts, tp = R.maxsim_topk(corpus, Q, k)
+        rs, rp = torch.sort(s_all, dim=1, descending=True, stable=True)
+        assert torch.equal(tp, rp[:, :k]) and torch.equal(ts, rs[:, :k])
+    assert [int(tp[b, 0]) for b in range(6)] == [0, 1, n_p // 2, n_p - 1, 77, n_p - 2]
+    assert torch.equal(s_all, R.maxsim_scores(corpus, Q))
+    try:
+        _cabi.check(L.flmr_debug_set_scan_variant(2))
+        s_single = R.maxsim_scores(corpus, Q)
+        _, tp_single = R.maxsim_topk(corpus, Q, 100)
+    finally:
+        L.flmr_debug_set_scan_variant(0)
+    np.testing.assert_allclose(s_all.cpu().numpy(), s_single.cpu().numpy(), rtol=2e-6)
+    assert torch.equal(tp, tp_single)
