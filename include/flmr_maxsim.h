@@ -323,11 +323,14 @@ int flmr_debug_build_partition(const int32_t* h_doclens, int64_t n_passages, int
                                int64_t tile_capacity, int64_t* n_tiles_out);
 
 /* Test infrastructure, host-only: the corpus passes flmr_maxsim_scores / flmr_maxsim_topk run for a batch of
- * `n_queries` queries of `nq` tokens (a pass = one scan-kernel launch with up to 640 query rows resident).
- * out_plan (may be NULL to query *n_passes_out) receives 8 int32 per pass: first query, queries resident,
- * first row, rows, 32-row blocks per query, 128-row tiles, flags (1 = adds earlier partial scores,
- * 2 = stores partial scores, 4 = final: scores complete, top-k taken), first query of its partial-score rows. */
-int flmr_debug_plan_passes(int n_queries, int nq, int32_t* out_plan, int capacity, int* n_passes_out);
+ * `n_queries` queries of `nq` tokens (a pass = one scan-kernel launch with up to 640 query rows resident per CTA);
+ * allow_pair != 0 plans CTA-pair passes (clusters of two CTAs share a token range, each with its own queries) for
+ * the query prefix that fills them, as the library does on shards that span every SM.
+ * out_plan (may be NULL to query *n_passes_out) receives 8 int32 per pass: first query, queries resident PER CTA (a
+ * pair pass covers twice as many: CTA r the r-th half), first row, rows, 32-row blocks per query, 128-row tiles per
+ * CTA, flags (1 = adds earlier partial scores, 2 = stores partial scores, 4 = final: scores complete, top-k taken,
+ * 8 = pair pass), row of the pass's first query in the partial-score buffer. */
+int flmr_debug_plan_passes(int n_queries, int nq, int allow_pair, int32_t* out_plan, int capacity, int* n_passes_out);
 
 /* Kernels launched by this library on the calling thread since the last reset (bench evidence). */
 int64_t flmr_launch_count(int reset);

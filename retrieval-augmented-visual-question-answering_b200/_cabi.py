@@ -110,7 +110,7 @@ def lib() -> C.CDLL:
     L.flmr_debug_set_argmax_path.argtypes = [i32]
     L.flmr_debug_set_scan_variant.argtypes = [i32]
     L.flmr_debug_build_partition.argtypes = [vp, i64, i32, vp, vp, vp, vp, i64, C.POINTER(i64)]
-    L.flmr_debug_plan_passes.argtypes = [i32, i32, vp, i32, C.POINTER(i32)]
+    L.flmr_debug_plan_passes.argtypes = [i32, i32, i32, vp, i32, C.POINTER(i32)]
     L.flmr_launch_count.restype = i64
     L.flmr_launch_count.argtypes = [i32]
     L.flmr_set_profiling.argtypes = [i32]

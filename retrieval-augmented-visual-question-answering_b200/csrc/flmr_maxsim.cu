@@ -294,12 +294,12 @@ __global__ void __launch_bounds__(kMergeThreads)
 flmr_merge_kernel(const uint64_t* __restrict__ keys, const float* __restrict__ in_scores,
                   const int64_t* __restrict__ in_pids, int n_lists, int n_queries, int k_in,
                   int k_out, int64_t pid_base, float* __restrict__ out_scores,
-                  int64_t* __restrict__ out_pids) {
+                  int64_t* __restrict__ out_pids, int q_offset) {
   __shared__ uint32_t s_ord[32];
   __shared__ int64_t s_pid[32];
   __shared__ uint32_t w_ord;
   __shared__ int64_t w_pid;
-  const int b = blockIdx.x;
+  const int b = q_offset + blockIdx.x;   // n_queries = stride of the per-list arrays; blocks cover [q_offset, q_offset + grid)
   const int n = n_lists * k_in;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   Cand c[kMergePer];
@@ -698,63 +698,95 @@ void build_partition(const std::vector<int64_t>& poff, int n_ctas, int tile_n,
 // ---- pass planning (pure host logic; exported for tests as flmr_debug_plan_passes) -------------------
 // One pass = one launch of the scan kernel over the whole shard with up to kRbMax 32-row blocks of
 // queries resident (kNqMax queries at most).
-enum : int { kPassAccIn = 1, kPassAccOut = 2, kPassFinal = 4 };
+enum : int { kPassAccIn = 1, kPassAccOut = 2, kPassFinal = 4, kPassPair = 8 };
 struct PassPlan {
-  int q_first, n_q;        // queries [q_first, q_first + n_q) are resident
+  int q_first, n_q;        // queries [q_first, q_first + n_q) are resident (pair pass: n_q PER CTA, the pass covers
+                           // [q_first, q_first + 2 n_q), CTA r of every pair the r-th half)
   int row0, rows;          // their rows [row0, row0 + rows)
-  int rbq, n_mtiles;       // 32-row blocks per query, 128-row MMA tiles of the pass
+  int rbq, n_mtiles;       // 32-row blocks per query, 128-row MMA tiles of the pass (per CTA)
   int flags;               // kPassAccIn: add the partial scores of earlier slices; kPassAccOut: store
-                           // partial scores; kPassFinal: scores complete -> top-k (+ all-scores output)
+                           // partial scores; kPassFinal: scores complete -> top-k (+ all-scores output);
+                           // kPassPair: CTA-pair pass (clusters of two CTAs share a token range)
   int group_first, acc_slot;  // row of the partial-score buffer: query group_first + acc_slot (+ i)
 };
 
-void plan_passes(int n_queries, int nq, std::vector<PassPlan>* out, int* group_out) {
+// allow_pair: CTA-pair passes (run_search decides: shards that span every SM) for as many queries as fill them —
+// every CTA of a pair keeps exactly the residency a normal pass would give it, so a pair pass serves twice the
+// queries per corpus pass; with fewer than four 128-row tiles per CTA pairs measured slower and are not planned.
+// Pair passes always cover a PREFIX of the queries (*n_pair_queries_out); the rest gets normal passes.
+void plan_passes(int n_queries, int nq, bool allow_pair, std::vector<PassPlan>* out, int* group_out,
+                 int* n_pair_queries_out) {
   out->clear();
+  int n_pair_q = 0;
   const int rbq_total = (nq + 31) / 32;
   if (rbq_total <= kRbMax) {
+    const int qpp_max = std::min(kNqMax, kRbMax / rbq_total);
+    if (allow_pair && qpp_max * rbq_total * 32 >= 4 * kTileM) {
+      for (; n_pair_q + 2 * qpp_max <= n_queries; n_pair_q += 2 * qpp_max)
+        out->push_back({n_pair_q, qpp_max, 0, nq, rbq_total, (qpp_max * rbq_total * 32 + kTileM - 1) / kTileM,
+                        kPassFinal | kPassPair, n_pair_q, 0});
+    }
     // whole queries resident: as many per pass as fit, spread evenly over the passes that takes (64
     // queries of one row block: 4 passes of 16 rather than 20+20+20+4, whose short last pass would be
     // HBM-bound while the others are tensor-bound)
-    const int qpp_max = std::min(kNqMax, kRbMax / rbq_total);
-    const int n_passes = (n_queries + qpp_max - 1) / qpp_max;
-    const int qpp = n_passes ? (n_queries + n_passes - 1) / n_passes : 1;
-    for (int b0 = 0; b0 < n_queries; b0 += qpp) {
+    const int rest = n_queries - n_pair_q;
+    const int n_passes = (rest + qpp_max - 1) / qpp_max;
+    const int qpp = n_passes ? (rest + n_passes - 1) / n_passes : 1;
+    for (int b0 = n_pair_q; b0 < n_queries; b0 += qpp) {
       const int nqp = std::min(qpp, n_queries - b0);
       out->push_back({b0, nqp, 0, nq, rbq_total, (nqp * rbq_total * 32 + kTileM - 1) / kTileM, kPassFinal,
                       b0, 0});
     }
     *group_out = 1;
+    if (n_pair_queries_out) *n_pair_queries_out = n_pair_q;
     return;
   }
   // queries longer than one pass holds: rows sliced over several passes, partial scores carried through
-  // HBM.  Full slices take one pass per query; the TAIL slices of up to `group` queries share one pass
-  // (Nq = 832: 3 queries = 3 full passes + 1 tail pass instead of 6).
+  // HBM.  Full slices take one pass per query (pair pass: per two queries, one in each CTA); the TAIL slices of up
+  // to `group` queries share one pass (Nq = 832: 3 queries = 3 full passes + 1 tail pass instead of 6; with pairs
+  // 6 queries = 3 full pair passes + 1 tail pair pass).
   const int rows_per_slice = kRbMax * 32;
   const int n_slices = (nq + rows_per_slice - 1) / rows_per_slice;
   const int tail_row0 = (n_slices - 1) * rows_per_slice;
   const int tail_rows = nq - tail_row0;
   const int tail_rbq = (tail_rows + 31) / 32;
-  const int group = std::max(1, std::min({kNqMax, kRbMax / tail_rbq, n_queries}));
-  for (int b0 = 0; b0 < n_queries; b0 += group) {
+  const int g_max = std::max(1, std::min(kNqMax, kRbMax / tail_rbq));
+  int group_used = 0;
+  if (allow_pair) {
+    const int G = 2 * g_max;                    // queries per pair group; a query's slot in the partial-score
+    for (; n_pair_q + G <= n_queries; n_pair_q += G) {   // buffer = its index in the group
+      const int b0 = n_pair_q;
+      for (int j = 0; j < g_max; ++j)           // queries b0 + 2j (CTA 0) and b0 + 2j + 1 (CTA 1)
+        for (int sl = 0; sl + 1 < n_slices; ++sl)
+          out->push_back({b0 + 2 * j, 1, sl * rows_per_slice, rows_per_slice, kRbMax, rows_per_slice / kTileM,
+                          kPassAccOut | (sl > 0 ? kPassAccIn : 0) | kPassPair, b0, 2 * j});
+      out->push_back({b0, g_max, tail_row0, tail_rows, tail_rbq, (g_max * tail_rbq * 32 + kTileM - 1) / kTileM,
+                      kPassAccIn | kPassFinal | kPassPair, b0, 0});
+      group_used = G;
+    }
+  }
+  const int rest = n_queries - n_pair_q;
+  const int group = std::max(1, std::min(g_max, rest));
+  for (int b0 = n_pair_q; b0 < n_queries; b0 += group) {
     const int g = std::min(group, n_queries - b0);
     for (int b = 0; b < g; ++b)
-      for (int s = 0; s + 1 < n_slices; ++s)
-        out->push_back({b0 + b, 1, s * rows_per_slice, rows_per_slice, kRbMax, rows_per_slice / kTileM,
-                        kPassAccOut | (s > 0 ? kPassAccIn : 0), b0, b});
+      for (int sl = 0; sl + 1 < n_slices; ++sl)
+        out->push_back({b0 + b, 1, sl * rows_per_slice, rows_per_slice, kRbMax, rows_per_slice / kTileM,
+                        kPassAccOut | (sl > 0 ? kPassAccIn : 0), b0, b});
     out->push_back({b0, g, tail_row0, tail_rows, tail_rbq, (g * tail_rbq * 32 + kTileM - 1) / kTileM,
                     kPassAccIn | kPassFinal, b0, 0});
+    group_used = std::max(group_used, g);
   }
-  *group_out = group;
+  *group_out = std::max(1, group_used);
+  if (n_pair_queries_out) *n_pair_queries_out = n_pair_q;
 }
 
-int launch_scan(const flmr_corpus* c, flmr_workspace* ws, const ScanParams& p, cudaStream_t st) {
-  // product instantiation unless a timing experiment / timestamp mode was requested
-  // (both instantiations got their dynamic-shared-memory limit raised in flmr_corpus_create)
+int launch_scan(const flmr_corpus* c, flmr_workspace* ws, ScanParams p, bool pair, cudaStream_t st) {
   // three epilogue warpgroups pay off exactly where they buy a third TMEM accumulator stage and one accumulator
-  // per warpgroup and D tile: passes with three resident query tiles (one Nq = 320 query: +12 %, 66 -> 74.5 q/s at
-  // 1M passages); with five tiles (2 / 2 / 1 accumulators per warpgroup, still two stages) they measured 7 % slower
+  // per warpgroup and D tile: passes with three resident query tiles (one Nq = 320 query: +12 % in short runs, +4 %
+  // sustained); with five tiles (2 / 2 / 1 accumulators per warpgroup, still two stages) they measured 7 % slower
   // than strict two-warpgroup alternation, with one, two or four tiles the same (profiles/r02_scan_variant_probe.md)
-  const bool three = (g_scan_variant == 3) || (g_scan_variant == 0 && p.n_mtiles == 3);
+  const bool three = !pair && ((g_scan_variant == 3) || (g_scan_variant == 0 && p.n_mtiles == 3));
 #ifdef FLMR_DEBUG
   auto kern = p.debug_mode ? flmr_scan_kernel<true> : flmr_scan_kernel<false>;
   const bool use3 = three && !p.debug_mode;
@@ -769,111 +801,12 @@ int launch_scan(const flmr_corpus* c, flmr_workspace* ws, const ScanParams& p, c
     FLMR_CUDA(cudaEventRecord(ev.a, st));
   }
   (void)ws;
-  if (use3)
-    flmr_scan3_kernel<<<c->n_ctas, kScan3Threads, ScanSmem::kBytes, st>>>(c->tmap_d, p);
-  else
-    kern<<<c->n_ctas, kScanThreads, ScanSmem::kBytes, st>>>(c->tmap_d, p);
-  FLMR_CUDA(cudaGetLastError());
-  ++g_launches;
-  if (g_profiling) {
-    FLMR_CUDA(cudaEventRecord(ev.b, st));
-    g_scan_events.push_back(ev);
-  }
-  return FLMR_OK;
-}
-
-// Stage passes [first, first + count) of `plan` into slots 0.. of the workspace's staging buffer.
-int stage_queries(flmr_workspace* ws, const void* d_q, int nq, const std::vector<PassPlan>& plan, size_t first,
-                  size_t count, cudaStream_t st) {
-  StageParams sp{};
-  for (size_t i = 0; i < count; ++i) {
-    const PassPlan& pp = plan[first + i];
-    sp.pass[i] = {pp.q_first, pp.n_q, pp.row0, pp.rows, pp.rbq, pp.n_mtiles * kTileM};
-  }
-  const int threads = 256;
-  dim3 grid((kMtMax * kTileM * 16 + threads - 1) / threads, static_cast<unsigned>(count));
-  flmr_stage_queries_kernel<<<grid, threads, 0, st>>>(reinterpret_cast<const uint4*>(d_q),
-                                                      reinterpret_cast<uint4*>(ws->d_qpad), nq, sp);
-  FLMR_CUDA(cudaGetLastError());
-  ++g_launches;
-  return FLMR_OK;
-}
-
-// One launch merges the per-CTA candidate lists of ALL queries of a call (block b = query b).
-int launch_merge_keys(const flmr_corpus* c, flmr_workspace* ws, int nq_pass, int k,
-                      float* d_out_scores, int64_t* d_out_pids, cudaStream_t st) {
-  if (static_cast<int64_t>(c->n_ctas) * k > kMergeThreads * kMergePer)
-    return fail(FLMR_ERR_UNSUPPORTED, "n_ctas*k = %lld exceeds merge capacity %d",
-                (long long)c->n_ctas * k, kMergeThreads * kMergePer);
-  flmr_merge_kernel<<<nq_pass, kMergeThreads, 0, st>>>(ws->d_cand_keys, nullptr, nullptr, c->n_ctas,
-                                                       nq_pass, k, k, c->pid_base, d_out_scores,
-                                                       d_out_pids);
-  FLMR_CUDA(cudaGetLastError());
-  ++g_launches;
-  return FLMR_OK;
-}
-
-// Partial-score rows of row-sliced (Nq > 640) queries: grown on demand, never shrunk.
-int ensure_acc(flmr_workspace* ws, int64_t floats) {
-  if (ws->acc_capacity >= floats) return FLMR_OK;
-  if (ws->d_acc) cudaFree(ws->d_acc);
-  ws->d_acc = nullptr;
-  ws->acc_capacity = 0;
-  FLMR_CUDA(cudaMalloc(reinterpret_cast<void**>(&ws->d_acc), static_cast<size_t>(floats) * sizeof(float)));
-  ws->acc_capacity = floats;
-  return FLMR_OK;
-}
-
-// CTA-pair passes: clusters of two CTAs stream one token range, each CTA with its own resident queries, every D tile
-// fetched from L2 / HBM once and TMA-multicast into both (flmr_scan_kernel<false, true>).  Each CTA keeps exactly the
-// residency a normal pass would give it (qpp_n queries, at least four 128-row tiles), so a pair pass serves
-// 2 * qpp_n queries per corpus pass: half the HBM / L2 traffic per query, and on this power-capped part ~6 % more
-// sustained throughput at the headline shape (profiles/r02_scan_variant_probe.md).  Handles the largest prefix of the
-// call that fills whole pair passes and returns its length in *handled (0: the call does not qualify); the caller
-// runs the remaining queries through normal passes.
-int run_search_pair(const flmr_corpus* c, flmr_workspace* ws, const void* d_q, int n_queries, int nq, ScanParams p,
-                    int k, float* d_all_scores, float* d_topk_scores, int64_t* d_topk_pids, cudaStream_t st,
-                    int* handled) {
-  *handled = 0;
-  const int rbq = (nq + 31) / 32;
-  if (c->n_pairs < 1 || rbq > kRbMax) return FLMR_OK;
-  const int h = std::min(kNqMax, kRbMax / rbq);               // queries per CTA = a normal pass's residency
-  if (h * rbq * 32 < 4 * kTileM) return FLMR_OK;               // fewer than four tiles per CTA: pairs measured slower
-  const int qpp = 2 * h;
-  int n_passes = std::min(n_queries, ws->max_queries) / qpp;
-  n_passes = std::min(n_passes, kStageMaxPasses / 2);
-  if (n_passes < 1) return FLMR_OK;
-  const int nq_handled = n_passes * qpp;
-  StageParams sp{};
-  for (int i = 0; i < 2 * n_passes; ++i) sp.pass[i] = {i * h, h, 0, nq, rbq, (h * rbq * 32 + kTileM - 1) / kTileM * kTileM};
-  {
-    const int threads = 256;
-    dim3 grid((kMtMax * kTileM * 16 + threads - 1) / threads, static_cast<unsigned>(2 * n_passes));
-    flmr_stage_queries_kernel<<<grid, threads, 0, st>>>(reinterpret_cast<const uint4*>(d_q),
-                                                        reinterpret_cast<uint4*>(ws->d_qpad), nq, sp);
-    FLMR_CUDA(cudaGetLastError());
-    ++g_launches;
-  }
-  p.cta_row_begin = c->d_pair_row_begin;
-  p.cta_tile_base = c->d_pair_tile_base;
-  p.tile_end_mask = c->d_pair_end_mask;
-  p.tile_first_pid = c->d_pair_first_pid;
-  p.cand_q_stride = nq_handled;
-  p.n_mtiles = (h * rbq * 32 + kTileM - 1) / kTileM;
-  p.nq_pass = h;
-  p.rbq = rbq;
-  p.acc_in = nullptr;
-  p.k = k;
-  for (int i = 0; i < n_passes; ++i) {
-    p.q_pad = reinterpret_cast<const uint4*>(ws->d_qpad) + static_cast<int64_t>(2 * i) * (kMtMax * kTileM * 16);
-    p.acc_out = d_all_scores ? d_all_scores + static_cast<int64_t>(i) * qpp * c->n_passages : nullptr;
-    p.cand_q_first = i * qpp;
-    EventPair ev{};
-    if (g_profiling) {
-      FLMR_CUDA(cudaEventCreate(&ev.a));
-      FLMR_CUDA(cudaEventCreate(&ev.b));
-      FLMR_CUDA(cudaEventRecord(ev.a, st));
-    }
+  if (pair) {
+    // clusters of two CTAs share one of the n_pairs token ranges; the tensor map has a half-tile box
+    p.cta_row_begin = c->d_pair_row_begin;
+    p.cta_tile_base = c->d_pair_tile_base;
+    p.tile_end_mask = c->d_pair_end_mask;
+    p.tile_first_pid = c->d_pair_first_pid;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(static_cast<unsigned>(2 * c->n_pairs));
     cfg.blockDim = dim3(kScanThreads);
@@ -887,21 +820,54 @@ int run_search_pair(const flmr_corpus* c, flmr_workspace* ws, const void* d_q, i
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     FLMR_CUDA(cudaLaunchKernelEx(&cfg, flmr_scan_kernel<false, true>, c->tmap_half, p));
-    ++g_launches;
-    if (g_profiling) {
-      FLMR_CUDA(cudaEventRecord(ev.b, st));
-      g_scan_events.push_back(ev);
-    }
+  } else if (use3) {
+    flmr_scan3_kernel<<<c->n_ctas, kScan3Threads, ScanSmem::kBytes, st>>>(c->tmap_d, p);
+  } else {
+    kern<<<c->n_ctas, kScanThreads, ScanSmem::kBytes, st>>>(c->tmap_d, p);
   }
-  if (k > 0) {
-    if (static_cast<int64_t>(c->n_pairs) * k > kMergeThreads * kMergePer)
-      return fail(FLMR_ERR_UNSUPPORTED, "n_pairs*k exceeds merge capacity");
-    flmr_merge_kernel<<<nq_handled, kMergeThreads, 0, st>>>(ws->d_cand_keys, nullptr, nullptr, c->n_pairs, nq_handled,
-                                                            k, k, c->pid_base, d_topk_scores, d_topk_pids);
-    FLMR_CUDA(cudaGetLastError());
-    ++g_launches;
+  FLMR_CUDA(cudaGetLastError());
+  ++g_launches;
+  if (g_profiling) {
+    FLMR_CUDA(cudaEventRecord(ev.b, st));
+    g_scan_events.push_back(ev);
   }
-  *handled = nq_handled;
+  return FLMR_OK;
+}
+
+// One launch stages `count` zero-padded query blocks (slot i of the workspace's staging buffer <- sp.pass[i]).
+int stage_queries(flmr_workspace* ws, const void* d_q, int nq, const StageParams& sp, int count, cudaStream_t st) {
+  const int threads = 256;
+  dim3 grid((kMtMax * kTileM * 16 + threads - 1) / threads, static_cast<unsigned>(count));
+  flmr_stage_queries_kernel<<<grid, threads, 0, st>>>(reinterpret_cast<const uint4*>(d_q),
+                                                      reinterpret_cast<uint4*>(ws->d_qpad), nq, sp);
+  FLMR_CUDA(cudaGetLastError());
+  ++g_launches;
+  return FLMR_OK;
+}
+
+// Queries [q0, q0 + nq) of a chunk of `stride` queries; `n_lists` = candidate lists per query (CTAs, or CTA pairs
+// for queries that went through pair passes).  d_out_* point at the chunk's first query.
+int launch_merge_keys(const flmr_corpus* c, flmr_workspace* ws, int n_lists, int stride, int q0, int nq, int k,
+                      float* d_out_scores, int64_t* d_out_pids, cudaStream_t st) {
+  if (nq <= 0) return FLMR_OK;
+  if (static_cast<int64_t>(n_lists) * k > kMergeThreads * kMergePer)
+    return fail(FLMR_ERR_UNSUPPORTED, "n_lists*k = %lld exceeds merge capacity %d",
+                (long long)n_lists * k, kMergeThreads * kMergePer);
+  flmr_merge_kernel<<<nq, kMergeThreads, 0, st>>>(ws->d_cand_keys, nullptr, nullptr, n_lists, stride, k, k,
+                                                  c->pid_base, d_out_scores, d_out_pids, q0);
+  FLMR_CUDA(cudaGetLastError());
+  ++g_launches;
+  return FLMR_OK;
+}
+
+// Partial-score rows of row-sliced (Nq > 640) queries: grown on demand, never shrunk.
+int ensure_acc(flmr_workspace* ws, int64_t floats) {
+  if (ws->acc_capacity >= floats) return FLMR_OK;
+  if (ws->d_acc) cudaFree(ws->d_acc);
+  ws->d_acc = nullptr;
+  ws->acc_capacity = 0;
+  FLMR_CUDA(cudaMalloc(reinterpret_cast<void**>(&ws->d_acc), static_cast<size_t>(floats) * sizeof(float)));
+  ws->acc_capacity = floats;
   return FLMR_OK;
 }
 
@@ -956,47 +922,50 @@ int run_search(const flmr_corpus* c, flmr_workspace* ws, const void* d_q, int n_
   }
 #endif
 
-  // CTA-pair passes for as many queries as fill whole pair passes (variant 0 = product: whenever the shard spans
-  // every SM; 4 = always when possible; 2 / 3 = never), normal passes for the rest
-  if (g_scan_variant == 4 || (g_scan_variant == 0 && c->n_pairs * 2 == c->sm_count)) {
-    int handled = 0;
-    if (int prc = run_search_pair(c, ws, d_q, n_queries, nq, p, k, d_all_scores, d_topk_scores, d_topk_pids, st,
-                                  &handled))
-      return prc;
-    if (handled > 0) {
-      if (handled == n_queries) return FLMR_OK;
-      d_q = static_cast<const __nv_bfloat16*>(d_q) + static_cast<int64_t>(handled) * nq * kDim;
-      if (d_all_scores) d_all_scores += static_cast<int64_t>(handled) * c->n_passages;
-      if (d_topk_scores) d_topk_scores += static_cast<int64_t>(handled) * k;
-      if (d_topk_pids) d_topk_pids += static_cast<int64_t>(handled) * k;
-      n_queries -= handled;
-    }
-  }
+  // CTA-pair passes (clusters of two CTAs stream one token range, each CTA with the residency of a normal pass, every
+  // D tile fetched once and TMA-multicast into both: half the HBM / L2 traffic per query, ~6 % more sustained
+  // throughput on this power-capped part, profiles/r02_scan_variant_probe.md) are planned for as many queries as fill
+  // them when the shard spans every SM (variant 0 = product), always when forced (4), never under 2 / 3.
+  const bool allow_pair = c->n_pairs > 0 && (g_scan_variant == 4 || (g_scan_variant == 0 && c->n_pairs * 2 == c->sm_count));
   // a call is processed in chunks of at most ws->max_queries queries (the candidate buffer's capacity);
-  // within a chunk: every pass's scan, then ONE merge launch over all of the chunk's queries
+  // within a chunk: every pass's scan, then the merge over the chunk's queries (one launch per kind of pass)
   std::vector<PassPlan> plan;
+  std::vector<int> slot;
   int rc;
   for (int c0 = 0; c0 < n_queries; c0 += ws->max_queries) {
     const int nqc = std::min(ws->max_queries, n_queries - c0);
     const __nv_bfloat16* d_qc = static_cast<const __nv_bfloat16*>(d_q) + static_cast<int64_t>(c0) * nq * kDim;
     float* d_all_c = d_all_scores ? d_all_scores + static_cast<int64_t>(c0) * c->n_passages : nullptr;
-    int group = 1;
-    plan_passes(nqc, nq, &plan, &group);
+    int group = 1, n_pair_q = 0;
+    plan_passes(nqc, nq, allow_pair, &plan, &group, &n_pair_q);
     if (!d_all_c && nq > kRbMax * 32 && (rc = ensure_acc(ws, static_cast<int64_t>(group) * c->n_passages)))
       return rc;
     p.cand_q_stride = nqc;
+    slot.assign(plan.size(), 0);
+    size_t staged_until = 0;                    // passes [0, staged_until) have their queries staged
     for (size_t pi = 0; pi < plan.size(); ++pi) {
+      if (pi == staged_until) {
+        // the query blocks of as many of the next passes as fit the staging buffer (a pair pass takes two slots:
+        // one block per CTA of a pair) are staged by ONE launch, ahead of their scans
+        StageParams sp{};
+        int used = 0;
+        while (staged_until < plan.size()) {
+          const PassPlan& q = plan[staged_until];
+          const int need = (q.flags & kPassPair) ? 2 : 1;
+          if (used + need > kStageMaxPasses) break;
+          slot[staged_until] = used;
+          for (int r = 0; r < need; ++r)
+            sp.pass[used++] = {q.q_first + r * q.n_q, q.n_q, q.row0, q.rows, q.rbq, q.n_mtiles * kTileM};
+          ++staged_until;
+        }
+        if ((rc = stage_queries(ws, d_qc, nq, sp, used, st))) return rc;
+      }
       const PassPlan& pp = plan[pi];
       // partial / final scores of query (group_first + acc_slot + i) live in row i of `acc`
       float* acc = d_all_c
                        ? d_all_c + static_cast<int64_t>(pp.group_first + pp.acc_slot) * c->n_passages
                        : (ws->d_acc ? ws->d_acc + static_cast<int64_t>(pp.acc_slot) * c->n_passages : nullptr);
-      // the queries of up to kStageMaxPasses passes are staged by ONE launch, ahead of their scans
-      if (pi % kStageMaxPasses == 0 &&
-          (rc = stage_queries(ws, d_qc, nq, plan, pi, std::min<size_t>(kStageMaxPasses, plan.size() - pi), st)))
-        return rc;
-      p.q_pad = reinterpret_cast<const uint4*>(ws->d_qpad) +
-                static_cast<int64_t>(pi % kStageMaxPasses) * (kMtMax * kTileM * 16);
+      p.q_pad = reinterpret_cast<const uint4*>(ws->d_qpad) + static_cast<int64_t>(slot[pi]) * (kMtMax * kTileM * 16);
       p.n_mtiles = pp.n_mtiles;
       p.nq_pass = pp.n_q;
       p.rbq = pp.rbq;
@@ -1004,11 +973,15 @@ int run_search(const flmr_corpus* c, flmr_workspace* ws, const void* d_q, int n_
       p.acc_out = ((pp.flags & kPassAccOut) || ((pp.flags & kPassFinal) && d_all_c)) ? acc : nullptr;
       p.k = (pp.flags & kPassFinal) ? k : 0;
       p.cand_q_first = pp.q_first;
-      if ((rc = launch_scan(c, ws, p, st))) return rc;
+      if ((rc = launch_scan(c, ws, p, (pp.flags & kPassPair) != 0, st))) return rc;
     }
-    if (k > 0 && (rc = launch_merge_keys(c, ws, nqc, k, d_topk_scores + static_cast<int64_t>(c0) * k,
-                                         d_topk_pids + static_cast<int64_t>(c0) * k, st)))
-      return rc;
+    if (k > 0) {
+      float* os = d_topk_scores + static_cast<int64_t>(c0) * k;
+      int64_t* op = d_topk_pids + static_cast<int64_t>(c0) * k;
+      // queries of pair passes have one candidate list per CTA PAIR, the others one per CTA
+      if ((rc = launch_merge_keys(c, ws, c->n_pairs, nqc, 0, n_pair_q, k, os, op, st))) return rc;
+      if ((rc = launch_merge_keys(c, ws, c->n_ctas, nqc, n_pair_q, nqc - n_pair_q, k, os, op, st))) return rc;
+    }
   }
   return FLMR_OK;
 }
@@ -1469,7 +1442,7 @@ int flmr_workspace_create(const flmr_corpus_t* c, int max_queries, int max_nq,
   if (max_nq > kRbMax * 32) {   // row-sliced queries expected: size their partial-score rows now
     std::vector<PassPlan> plan;
     int group = 1;
-    plan_passes(max_queries, max_nq, &plan, &group);
+    plan_passes(max_queries, max_nq, c->n_pairs > 0, &plan, &group, nullptr);
     if (int rc = ensure_acc(ws, static_cast<int64_t>(group) * c->n_passages)) return bail(rc);
   }
 #ifdef FLMR_DEBUG
@@ -1528,7 +1501,7 @@ int flmr_topk_merge(const float* d_in_scores, const int64_t* d_in_pids, int n_li
   DeviceGuard guard(device);
   if (!guard.ok) return fail(FLMR_ERR_CUDA, "cudaSetDevice(%d) failed", device);
   flmr_merge_kernel<<<n_queries, kMergeThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-      nullptr, d_in_scores, d_in_pids, n_lists, n_queries, k_in, k_out, 0, d_out_scores, d_out_pids);
+      nullptr, d_in_scores, d_in_pids, n_lists, n_queries, k_in, k_out, 0, d_out_scores, d_out_pids, 0);
   FLMR_CUDA(cudaGetLastError());
   ++g_launches;
   return FLMR_OK;
@@ -1893,11 +1866,11 @@ int flmr_debug_build_partition(const int32_t* h_doclens, int64_t n_passages, int
   return FLMR_OK;
 }
 
-int flmr_debug_plan_passes(int n_queries, int nq, int32_t* out_plan, int capacity, int* n_passes_out) {
+int flmr_debug_plan_passes(int n_queries, int nq, int allow_pair, int32_t* out_plan, int capacity, int* n_passes_out) {
   if (n_queries < 0 || nq <= 0 || !n_passes_out) return fail(FLMR_ERR_INVALID_ARG, "bad argument");
   std::vector<PassPlan> plan;
   int group = 1;
-  plan_passes(n_queries, nq, &plan, &group);
+  plan_passes(n_queries, nq, allow_pair != 0, &plan, &group, nullptr);
   *n_passes_out = static_cast<int>(plan.size());
   if (out_plan) {
     if (static_cast<int>(plan.size()) > capacity)
@@ -2019,7 +1992,7 @@ int flmr_topk_exchange(flmr_comm_t* c, const float* d_scores, const int64_t* d_p
   if (r1 != 0 || r2 != 0)
     return fail(FLMR_ERR_CUDA, "ncclAllGather failed: %s", api->GetErrorString(r1 ? r1 : r2));
   flmr_merge_kernel<<<n_queries, kMergeThreads, 0, st>>>(nullptr, c->d_recv_s, c->d_recv_p, c->world, n_queries,
-                                                        k_in, k_out, 0, d_out_scores, d_out_pids);
+                                                        k_in, k_out, 0, d_out_scores, d_out_pids, 0);
   FLMR_CUDA(cudaGetLastError());
   ++g_launches;
   return FLMR_OK;

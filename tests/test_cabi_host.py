@@ -130,12 +130,13 @@ def test_partition_invariants(seed, n, lo, hi, ctas):
     assert np.all(np.diff(rb) <= share + plen.max() + 1)
 
 
-def _plan(n_queries, nq):
+def _plan(n_queries, nq, allow_pair=0):
     L = _cabi.lib()
     n = C.c_int(0)
-    _cabi.check(L.flmr_debug_plan_passes(n_queries, nq, None, 0, C.byref(n)))
+    _cabi.check(L.flmr_debug_plan_passes(n_queries, nq, allow_pair, None, 0, C.byref(n)))
     buf = np.zeros((max(n.value, 1), 8), dtype=np.int32)
-    _cabi.check(L.flmr_debug_plan_passes(n_queries, nq, buf.ctypes.data_as(C.c_void_p), n.value, C.byref(n)))
+    _cabi.check(L.flmr_debug_plan_passes(n_queries, nq, allow_pair, buf.ctypes.data_as(C.c_void_p), n.value,
+                                         C.byref(n)))
     return buf[: n.value]
 
 
@@ -193,6 +194,69 @@ def test_pass_plan_random_shapes():
             if flags & 4:
                 final[q_first:q_first + n_q] += 1
         assert (covered == 1).all() and (final == 1).all(), (n_queries, nq)
+
+
+@pytest.mark.parametrize("n_queries,nq", [(4, 320), (16, 320), (5, 320), (3, 320), (64, 32), (40, 32), (41, 32),
+                                           (16, 832), (6, 832), (7, 832), (5, 832), (13, 1500), (2, 1280), (9, 641),
+                                           (8, 128), (3, 45), (0, 64), (44, 200)])
+def test_pass_plan_with_cta_pairs(n_queries, nq):
+    """With CTA-pair passes allowed: pair passes (flag 8) cover a PREFIX of the queries, two blocks of n_q queries
+    each (CTA r of every pair the r-th block), each CTA with at least four 128-row tiles when whole queries are
+    resident; the rest of the batch is planned exactly like a batch of that size without pairs; every (query, row)
+    is still resident exactly once, partial scores are read only after they were written, and within one group of
+    row-sliced queries no two queries share a partial-score row."""
+    plan = _plan(n_queries, nq, 1)
+    ACC_IN, ACC_OUT, FINAL, PAIR = 1, 2, 4, 8
+    covered = np.zeros((n_queries, nq), dtype=np.int32)
+    touched = np.zeros(n_queries, dtype=bool)
+    finalised = np.zeros(n_queries, dtype=bool)
+    acc_row = np.full(n_queries, -1)
+    n_pair_q, seen_single = 0, False
+    for q_first, n_q, row0, rows, rbq, n_mtiles, flags, acc_first in plan:
+        pair = bool(flags & PAIR)
+        span = 2 * n_q if pair else n_q
+        assert 1 <= n_q <= 20 and rbq == (rows + 31) // 32 and n_q * rbq <= 20
+        assert n_mtiles == (n_q * rbq * 32 + 127) // 128 and 1 <= n_mtiles <= 5
+        assert 0 <= row0 and row0 + rows <= nq and row0 % 32 == 0 and q_first + span <= n_queries
+        if pair:
+            assert not seen_single                            # pair passes first
+            n_pair_q = max(n_pair_q, q_first + span)
+            if nq <= 640:
+                assert n_mtiles >= 4                          # pairs only where a CTA is tensor-bound on its own
+        else:
+            seen_single = True
+            assert q_first >= n_pair_q
+        qs = slice(q_first, q_first + span)
+        assert not finalised[qs].any()
+        assert bool(flags & ACC_IN) == bool(touched[qs].all()) and touched[qs].all() == touched[qs].any()
+        if not flags & FINAL:
+            assert flags & ACC_OUT
+        rows_here = acc_first + np.arange(span)               # partial-score row of query q_first + i
+        assert (acc_row[qs] < 0).all() or (acc_row[qs] == rows_here).all()
+        acc_row[qs] = rows_here
+        covered[qs, row0:row0 + rows] += 1
+        touched[qs] = True
+        if flags & FINAL:
+            finalised[qs] = True
+    assert (covered == 1).all() and finalised.all()
+    # the queries after the pair prefix: the plan of a (n_queries - n_pair_q)-query batch, shifted
+    rest = _plan(n_queries - n_pair_q, nq, 0)
+    tail = np.array([p for p in plan if not p[6] & PAIR]).reshape(-1, 8)
+    if len(rest):
+        shifted = rest.copy()
+        shifted[:, 0] += n_pair_q
+        shifted[:, 7] += n_pair_q
+        assert np.array_equal(tail, shifted)
+    else:
+        assert len(tail) == 0
+    # pairs halve the corpus passes of the prefix
+    if n_pair_q:
+        assert len(plan) - len(tail) == len(_plan(n_pair_q, nq, 0)) // 2 or nq > 640
+        if nq > 640:
+            n_slices = -(-nq // 640)
+            g = max(1, min(20, 20 // ((nq - (n_slices - 1) * 640 + 31) // 32)))
+            assert n_pair_q % (2 * g) == 0
+            assert len(plan) - len(tail) == (n_pair_q // (2 * g)) * (g * (n_slices - 1) + 1)
 
 
 def test_comm_entry_points_validate_arguments():

@@ -282,7 +282,10 @@ def test_topk_select_kernel(R):
     (3000, 60, 1, 32, True, False, 5), (3000, 60, 2, 64, True, True, 7), (2000, 180, 1, 320, False, False, 5),
     (2000, 180, 2, 320, True, False, 100), (1500, 90, 3, 129, True, False, 5), (1200, 100, 5, 97, True, False, 3),
     (900, 64, 20, 32, True, False, 5), (700, 50, 3, 832, True, False, 10), (5, 7, 2, 320, True, False, 5),
-    (2500, 13, 2, 320, True, False, 5), (800, 200, 16, 320, True, False, 5)])
+    (2500, 13, 2, 320, True, False, 5), (800, 200, 16, 320, True, False, 5),
+    # row-sliced queries under CTA pairs: 6 queries of Nq = 832 per pair group (+1 left over), 4 of Nq = 1500 (+1),
+    # and Nq = 641 whose one-row tails fill a pair group only from 40 queries up
+    (700, 50, 7, 832, True, False, 10), (600, 40, 5, 1500, True, True, 5), (400, 30, 43, 641, True, False, 4)])
 def test_three_warpgroup_scan_kernel_is_bit_identical(case):
     """flmr_scan3_kernel (three epilogue warpgroups, static query-tile assignment, 2-4 TMEM stages; the product
     uses it for passes with three resident query tiles) forced onto every pass shape: scores and fused top-k
@@ -351,7 +354,7 @@ def test_big_cta_pair_passes_properties(R, big):
         Q[b, :32] = D[t * nd: t * nd + 32]
     L.flmr_launch_count(1)
     s_all = R.maxsim_scores(corpus, Q)
-    assert L.flmr_launch_count(1) == 4                                    # (staging + pair pass of 4) + (staging + normal pass of 2)
+    assert L.flmr_launch_count(1) == 3                                    # one staging launch + pair pass of 4 + normal pass of 2
     for k in (5, 100):
         ts, tp = R.maxsim_topk(corpus, Q, k)
         rs, rp = torch.sort(s_all, dim=1, descending=True, stable=True)
