@@ -723,10 +723,13 @@ def c4_record(dev, world, rank):
     lens = torch.randint(nd // 2, nd + 1, (B * nway,), generator=g)
     mask = (torch.arange(nd)[None, :] < lens[:, None]).unsqueeze(-1).to(dev)
 
-    def timed(cross, reps=20):
+    def timed(cross, reps=20, loss_fn=None):
         def step():
             Q.grad = D.grad = None
-            R.in_batch_negatives_loss(Q, D, mask, nway, cross_rank_negatives=cross).backward()
+            if loss_fn is not None:
+                loss_fn(Q, D, mask).backward()
+            else:
+                R.in_batch_negatives_loss(Q, D, mask, nway, cross_rank_negatives=cross).backward()
         for _ in range(3):
             step()
         if world > 1:
@@ -747,6 +750,11 @@ def c4_record(dev, world, rank):
     rec = {"workload": "MaxSim in-batch-negatives loss, forward + backward: %d ranks x (8 queries x 16 documents), "
                        "Nq=832, Nd=512 ragged, d=128 (bsz %d)" % (world, 8 * world),
            "local_negatives_ms": timed(False), "unit": "ms per step, max over ranks"}
+    try:   # the same step with forward and backward replayed as CUDA graphs (fixed batch shape)
+        rec["local_negatives_cuda_graphs_ms"] = timed(False, loss_fn=R.graphed_in_batch_negatives_loss(Q, D, mask, nway))
+    except Exception as e:   # a record, not a gate: the eager figure above stands on its own
+        rec["local_negatives_cuda_graphs_ms"] = None
+        rec["cuda_graphs_error"] = repr(e)[:200]
     if world > 1:
         rec["cross_rank_negatives_ms"] = timed(True)
         rec["cross_rank_matrix"] = "[8, %d] per rank" % (B * nway * world)

@@ -273,6 +273,27 @@ def in_batch_negatives_loss(Q: torch.Tensor, D_padded: torch.Tensor, D_mask: tor
     return (loss, scores) if return_scores else loss
 
 
+def graphed_in_batch_negatives_loss(Q: torch.Tensor, D_padded: torch.Tensor, D_mask: torch.Tensor, nway: int,
+                                    num_warmup_iters: int = 3):
+    """CUDA-graph form of ``in_batch_negatives_loss`` for a training loop whose batch shape is fixed (the reference's
+    is: bsz / nranks queries x nway documents of fixed padded lengths, colbert.py:64-113).
+
+    The eager loss step is host-bound — its three kernels take less than half of the ~0.25 ms the autograd function,
+    the casts and the allocator need to launch them — so forward and backward are each captured once
+    (``torch.cuda.make_graphed_callables``: every launch of the C ABI goes to the capturing stream, nothing in the
+    path synchronises or allocates outside torch's and the library's stream-ordered pools) and replayed afterwards.
+    The arguments are samples of the right shape / dtype / ``requires_grad``; returns ``loss_fn(Q, D_padded, D_mask)
+    -> loss`` that takes part in autograd like the eager function (the encoders around it stay eager)."""
+    if not Q.is_cuda:
+        raise RuntimeError("graphed_in_batch_negatives_loss needs CUDA tensors (there is no CPU path)")
+    nway = int(nway)
+
+    def loss_fn(q, d, m):
+        return in_batch_negatives_loss(q, d, m, nway)
+
+    return torch.cuda.make_graphed_callables(loss_fn, (Q, D_padded, D_mask), num_warmup_iters=num_warmup_iters)
+
+
 class FLMRModelForRetrieval(torch.nn.Module):
     """Façade with the name the reference announces for its HF API (README.md:25) and the call surface
     of the in-repo ``FLMR*`` classes (src/models/retriever/FLMR.py): ``query`` / ``doc`` delegate to the

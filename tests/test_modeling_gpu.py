@@ -332,3 +332,29 @@ def test_tcgen05_argmax_many_documents_per_cta_back_to_back(argmax_path):
     for a2, m2 in outs:
         assert torch.equal(m2, m1)
         assert (a2 == a1).float().mean().item() > 0.9999
+
+
+def test_graphed_loss_step_replays_the_eager_step(argmax_path):
+    """graphed_in_batch_negatives_loss (forward and backward captured as CUDA graphs): on NEW inputs of the captured
+    shape the replayed loss and gradients equal the eager step's — both kernels of the forward (warp-MMA for the
+    C4 rank shape, tcgen05 forced) are capturable: no host synchronisation, stream-ordered scratch only."""
+    import ravqa_b200 as R
+    B, nway, nq, nd = 8, 2, 832, 512
+    Q, D, mask = _inputs(B, nq, B * nway, nd, seed=31)
+    m3 = mask.unsqueeze(-1)
+    for path in (0, 2):
+        argmax_path(path)
+        Qs, Ds = Q.clone().requires_grad_(True), D.clone().requires_grad_(True)
+        graphed = R.graphed_in_batch_negatives_loss(Qs, Ds, m3, nway)
+        for seed in (32, 33):
+            Q2, D2, mask2 = _inputs(B, nq, B * nway, nd, seed=seed)
+            Qa, Da = Q2.clone().requires_grad_(True), D2.clone().requires_grad_(True)
+            Qb, Db = Q2.clone().requires_grad_(True), D2.clone().requires_grad_(True)
+            la = R.in_batch_negatives_loss(Qa, Da, mask2.unsqueeze(-1), nway)
+            (la * 1.7).backward()
+            lb = graphed(Qb, Db, mask2.unsqueeze(-1))
+            (lb * 1.7).backward()
+            assert torch.equal(la.detach(), lb.detach())
+            assert torch.equal(Qa.grad, Qb.grad)
+            # dD is scattered with fp32 atomics: equal up to the order of the additions
+            np.testing.assert_allclose(Da.grad.cpu().numpy(), Db.grad.cpu().numpy(), rtol=1e-5, atol=1e-7)

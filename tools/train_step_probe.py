@@ -89,6 +89,35 @@ def single_gpu():
         ref_loss(Qg, Dg, m3, nway).backward()
     t_s = timed(step)
     t_r = timed(ref, reps=5)
+    # the same step with forward and backward captured as CUDA graphs (autograd-aware: make_graphed_callables) ...
+    graphed = R.graphed_in_batch_negatives_loss(Qg, Dg, m3, nway)
+
+    def step_graphed():
+        Qg.grad = Dg.grad = None
+        graphed(Qg, Dg, m3).backward()
+    t_g = timed(step_graphed)
+    # ... and as ONE graph of forward + backward over static buffers (what a fully captured training step replays)
+    Qs, Ds = Q.clone().requires_grad_(True), D.clone().requires_grad_(True)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            Qs.grad = Ds.grad = None
+            R.in_batch_negatives_loss(Qs, Ds, m3, nway).backward()
+    torch.cuda.current_stream().wait_stream(side)
+    whole = torch.cuda.CUDAGraph()
+    Qs.grad = Ds.grad = None
+    with torch.cuda.graph(whole):
+        loss_static = R.in_batch_negatives_loss(Qs, Ds, m3, nway)
+        loss_static.backward()
+    t_w = timed(whole.replay)
+    Qg.grad = Dg.grad = None
+    eager_loss = R.in_batch_negatives_loss(Qg, Dg, m3, nway)
+    eager_loss.backward()
+    whole.replay()
+    torch.cuda.synchronize()
+    same = (torch.equal(eager_loss.detach(), loss_static.detach()) and torch.equal(Qg.grad, Qs.grad)
+            and torch.allclose(Dg.grad, Ds.grad, rtol=1e-5, atol=1e-7))
     # where the host time of a step goes (CPU-side cost of each call, launches are asynchronous)
     import time
     from ravqa_b200 import modeling
@@ -119,6 +148,10 @@ def single_gpu():
     print("| sum of the kernels | %.3f |" % (t_f + t_l + t_b))
     print("| whole step: in_batch_negatives_loss(...).backward() incl. casts and autograd | %.3f (kernels = %.0f %%) |"
           % (t_s, 100 * (t_f + t_l + t_b) / t_s))
+    print("| the same step, forward and backward replayed as CUDA graphs (graphed_in_batch_negatives_loss) | %.3f "
+          "(kernels = %.0f %%) |" % (t_g, 100 * (t_f + t_l + t_b) / t_g))
+    print("| the same step as ONE captured graph of forward + backward (static buffers; loss and gradients equal "
+          "to eager: %s) | %.3f (kernels = %.0f %%) |" % (same, t_w, 100 * (t_f + t_l + t_b) / t_w))
     print("| torch restatement of compute_ib_loss_new (fp32, materialised) | %.3f |" % t_r)
 
 
