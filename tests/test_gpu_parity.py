@@ -369,3 +369,38 @@ def test_big_cta_pair_passes_properties(R, big):
         L.flmr_debug_set_scan_variant(0)
     np.testing.assert_allclose(s_all.cpu().numpy(), s_single.cpu().numpy(), rtol=2e-6)
     assert torch.equal(tp, tp_single)
+
+
+def test_search_call_is_cuda_graph_capturable(R):
+    """flmr_maxsim_topk / flmr_maxsim_scores enqueue their launches (query staging, single-CTA and cluster scan
+    passes, merges) on the caller's stream and synchronise nothing: a call captured into a CUDA graph and replayed
+    on NEW query contents gives exactly what the eager call gives — whole queries, CTA-pair passes forced, and
+    row-sliced queries whose partial scores live in the workspace."""
+    from ravqa_b200 import _cabi
+    L = _cabi.lib()
+    for (n, nd, B, nq, k, variant) in [(3000, 60, 5, 97, 7, 0), (2000, 120, 6, 320, 10, 4), (900, 50, 7, 832, 5, 4)]:
+        Q0, D, dl = O.synth(n, nd, B, nq, seed=17 + nq, ragged=True)
+        corpus = R.FlatCorpus(torch.from_numpy(D).to(torch.bfloat16), dl, device=0)
+        try:
+            _cabi.check(L.flmr_debug_set_scan_variant(variant))
+            Qs = torch.from_numpy(Q0).cuda().bfloat16()
+            R.maxsim_topk(corpus, Qs, k)                      # first call outside capture (sizes the workspace)
+            R.maxsim_scores(corpus, Qs)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                gs, gp = R.maxsim_topk(corpus, Qs, k)
+                ga = R.maxsim_scores(corpus, Qs)
+            for seed in (1, 2):
+                Q1, _, _ = O.synth(4, 4, B, nq, seed=seed)
+                Qs.copy_(torch.from_numpy(Q1).cuda().bfloat16())
+                graph.replay()
+                torch.cuda.synchronize()
+                es, ep = R.maxsim_topk(corpus, Qs, k)
+                ea = R.maxsim_scores(corpus, Qs)
+                assert torch.equal(gs, es) and torch.equal(gp, ep) and torch.equal(ga, ea)
+                ref = O.maxsim_scores(Q1, D, dl)
+                np.testing.assert_allclose(ga.cpu().numpy(), ref, rtol=2e-5)
+        finally:
+            L.flmr_debug_set_scan_variant(0)
+            corpus.close()
