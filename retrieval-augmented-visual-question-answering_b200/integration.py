@@ -46,8 +46,16 @@ def colbert_score_packed(Q, D_packed, D_lengths, config=None):
         Q = Q.squeeze(0)
     assert Q.dim() == 2, Q.size()
     assert D_packed.dim() == 2, D_packed.size()
-    relu = config is not None and getattr(config, "total_visible_gpus", 1) == 0 \
-        and getattr(config, "interaction", "colbert") != "flipr"
+    if config is not None and getattr(config, "interaction", "colbert") == "flipr":
+        # colbert.py:306-309: the 'flipr' reduction always takes the padded route; here: pad, then the arg-max
+        # launch + selection of modeling.colbert_score
+        lengths = torch.as_tensor(D_lengths).long().to(D_packed.device)
+        n, nd = int(lengths.numel()), int(lengths.max())
+        mask = torch.arange(nd, device=D_packed.device)[None, :] < lengths[:, None]
+        D_padded = D_packed.new_zeros((n, nd, D_packed.size(1)))
+        D_padded[mask] = D_packed[: int(lengths.sum())]
+        return colbert_score(Q.unsqueeze(0), D_padded, mask.unsqueeze(-1), config=config)
+    relu = config is not None and getattr(config, "total_visible_gpus", 1) == 0
     dev = torch.device("cuda", torch.cuda.current_device())
     corpus = FlatCorpus(D_packed.to(dev), torch.as_tensor(D_lengths).cpu(), device=dev)
     try:

@@ -62,12 +62,41 @@ def _forward_scores(Q: torch.Tensor, D_padded: torch.Tensor, D_mask: torch.Tenso
     return scores, mask, None
 
 
+def _flipr_reduce(rowmax: torch.Tensor, arg: torch.Tensor, query_maxlen: int):
+    """The ``interaction == 'flipr'`` branch of colbert_score_reduce (colbert.py:248-261) on the per-token maxima
+    ``rowmax [..., Nq]``: the sum of the ``K1 = query_maxlen // 2`` largest of the first ``query_maxlen`` tokens
+    plus, when at least ``K2 = 8`` tokens follow them, the sum of the 8 largest of the rest.  Returns (scores,
+    winners with the unselected tokens set to -1): the gradient reaches the selected tokens only, which is what
+    autograd through the reference's ``topk(...).values.sum()`` does, and the backward kernels skip winners < 0."""
+    assert query_maxlen == 64, ("for now", query_maxlen)                 # the reference's own restriction (:249)
+    K1, K2 = query_maxlen // 2, 8
+    keep = torch.zeros_like(rowmax, dtype=torch.bool)
+    top, idx = rowmax[..., :query_maxlen].topk(K1, dim=-1)
+    keep[..., :query_maxlen].scatter_(-1, idx, True)
+    scores = top.sum(dim=-1)
+    if K2 <= rowmax.size(-1) - query_maxlen:
+        top2, idx2 = rowmax[..., query_maxlen:].topk(K2, dim=-1)
+        keep[..., query_maxlen:].scatter_(-1, idx2, True)
+        scores = scores + top2.sum(dim=-1)
+    return scores, torch.where(keep, arg, torch.full_like(arg, -1))
+
+
 class _AllPairsMaxSim(torch.autograd.Function):
     """scores[b, p] = sum_i max_{j: mask[p, j]} <Q[b, i], D[p, j]>  for all (b, p)."""
 
     @staticmethod
-    def forward(ctx, Q: torch.Tensor, D_padded: torch.Tensor, D_mask: torch.Tensor) -> torch.Tensor:
-        scores, mask, arg = _forward_scores(Q, D_padded, D_mask)
+    def forward(ctx, Q: torch.Tensor, D_padded: torch.Tensor, D_mask: torch.Tensor, flipr_maxlen: int = 0
+                ) -> torch.Tensor:
+        if flipr_maxlen:
+            n, nd = D_padded.size(0), D_padded.size(1)
+            if float(Q.size(0)) * n * Q.size(1) * 8 > _FUSED_MAX_ARG_BYTES:
+                raise ValueError("interaction='flipr' keeps the per-token maxima of every pair: at most %d "
+                                 "(query row, document) pairs per call" % (_FUSED_MAX_ARG_BYTES // 8))
+            mask = D_mask.reshape(n, nd).bool()
+            arg, rowmax = maxsim_argmax(Q, D_padded, mask, return_rowmax=True)
+            scores, arg = _flipr_reduce(rowmax, arg, flipr_maxlen)
+        else:
+            scores, mask, arg = _forward_scores(Q, D_padded, D_mask)
         ctx.has_arg = arg is not None
         ctx.save_for_backward(Q, D_padded, mask, *([arg] if ctx.has_arg else []))
         return scores
@@ -77,11 +106,11 @@ class _AllPairsMaxSim(torch.autograd.Function):
         Q, D_padded, mask = ctx.saved_tensors[:3]
         need_dq, need_dd = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         if not (need_dq or need_dd):
-            return None, None, None
+            return None, None, None, None
         arg = ctx.saved_tensors[3] if ctx.has_arg else maxsim_argmax(Q, D_padded, mask)
         dQ, dD = maxsim_backward(Q, D_padded, arg, grad, need_dq=need_dq, need_dd=need_dd)
         return (dQ.to(Q.dtype) if dQ is not None else None,
-                dD.to(D_padded.dtype) if dD is not None else None, None)
+                dD.to(D_padded.dtype) if dD is not None else None, None, None)
 
 
 def _equal_run_length(Q: torch.Tensor) -> int:
@@ -109,32 +138,38 @@ class _GroupedMaxSim(torch.autograd.Function):
     pairs (one launch of the grouped arg-max kernel forward, saved winners, gather/scatter backward)."""
 
     @staticmethod
-    def forward(ctx, Q: torch.Tensor, D_padded: torch.Tensor, D_mask: torch.Tensor, r: int) -> torch.Tensor:
+    def forward(ctx, Q: torch.Tensor, D_padded: torch.Tensor, D_mask: torch.Tensor, r: int,
+                flipr_maxlen: int = 0) -> torch.Tensor:
         n, nd = D_padded.size(0), D_padded.size(1)
         mask = D_mask.reshape(n, nd).bool()
         arg, rowmax = maxsim_argmax_grouped(Q, D_padded, mask, r, return_rowmax=True)
+        if flipr_maxlen:
+            scores, arg = _flipr_reduce(rowmax, arg, flipr_maxlen)
+        else:
+            scores = rowmax.sum(dim=-1)                                        # [B, r]
         ctx.save_for_backward(Q, D_padded, arg)
-        return rowmax.sum(dim=-1)                                              # [B, r]
+        return scores
 
     @staticmethod
     def backward(ctx, grad: torch.Tensor):
         Q, D_padded, arg = ctx.saved_tensors
         need_dq, need_dd = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         if not (need_dq or need_dd):
-            return None, None, None, None
+            return None, None, None, None, None
         dQ, dD = maxsim_backward_grouped(Q, D_padded, arg, grad, need_dq=need_dq, need_dd=need_dd)
         return (dQ.to(Q.dtype) if dQ is not None else None,
-                dD.to(D_padded.dtype) if dD is not None else None, None, None)
+                dD.to(D_padded.dtype) if dD is not None else None, None, None, None)
 
 
 def grouped_maxsim(Q: torch.Tensor, D_padded: torch.Tensor, D_mask: torch.Tensor, docs_per_query: int
                    ) -> torch.Tensor:
     """``[B, r]`` scores of every query against its own ``r = docs_per_query`` documents (differentiable):
     ``ColBERT.score(Q.repeat_interleave(r, 0), D, D_mask).view(B, r)`` (colbert.py:71-73) without the repeat."""
-    return _GroupedMaxSim.apply(Q, D_padded, D_mask, int(docs_per_query))
+    return _GroupedMaxSim.apply(Q, D_padded, D_mask, int(docs_per_query), 0)
 
 
-def _aligned_maxsim(Q: torch.Tensor, D_padded: torch.Tensor, D_mask: torch.Tensor) -> torch.Tensor:
+def _aligned_maxsim(Q: torch.Tensor, D_padded: torch.Tensor, D_mask: torch.Tensor, flipr_maxlen: int = 0
+                    ) -> torch.Tensor:
     """scores[p] = MaxSim(Q[p], D[p]) for ``Q [n, Nq, d]`` aligned with ``D [n, Nd, d]``.
 
     Callers build ``Q`` with ``repeat_interleave`` (colbert.py:71, rag_model_blip.py:433,
@@ -146,8 +181,8 @@ def _aligned_maxsim(Q: torch.Tensor, D_padded: torch.Tensor, D_mask: torch.Tenso
     r = _equal_run_length(Q)
     if r:
         # differentiable pick of one representative per run; its gradient is the sum over the run's rows
-        return _GroupedMaxSim.apply(Q[::r], D_padded, D_mask, r).reshape(n)
-    return _GroupedMaxSim.apply(Q, D_padded, D_mask, 1).reshape(n)
+        return _GroupedMaxSim.apply(Q[::r], D_padded, D_mask, r, flipr_maxlen).reshape(n)
+    return _GroupedMaxSim.apply(Q, D_padded, D_mask, 1, flipr_maxlen).reshape(n)
 
 
 class _FusedIBLoss(torch.autograd.Function):
@@ -180,7 +215,7 @@ class _FusedIBLoss(torch.autograd.Function):
 
 def all_pairs_maxsim(Q: torch.Tensor, D_padded: torch.Tensor, D_mask: torch.Tensor) -> torch.Tensor:
     """``[B, n]`` MaxSim of every query against every padded document (differentiable)."""
-    return _AllPairsMaxSim.apply(Q, D_padded, D_mask)
+    return _AllPairsMaxSim.apply(Q, D_padded, D_mask, 0)
 
 
 def colbert_score(Q: torch.Tensor, D_padded: torch.Tensor, D_mask: torch.Tensor, config=None,
@@ -189,17 +224,22 @@ def colbert_score(Q: torch.Tensor, D_padded: torch.Tensor, D_mask: torch.Tensor,
 
     ``Q.size(0)`` is 1 (compare with all documents) or ``n`` (each query against its aligned
     document — callers build it with ``repeat_interleave``).  Returns ``[n]`` scores, true-max
-    semantics of the padded path."""
+    semantics of the padded path.  ``config.interaction == 'flipr'`` (colbert.py:248-261; FLMR uses the default
+    'colbert') reduces the per-token maxima by partial top-k sums instead of the plain sum: same arg-max launch,
+    the selection on its ``[n, Nq]`` output."""
     assert Q.dim() == 3 and D_padded.dim() == 3, (Q.size(), D_padded.size())
     assert Q.size(0) in [1, D_padded.size(0)]
+    interaction = getattr(config, "interaction", "colbert") if config is not None else "colbert"
+    assert interaction in ["colbert", "flipr"], interaction                  # colbert.py:246
+    flipr_maxlen = int(config.query_maxlen) if interaction == "flipr" else 0
     del config, use_gpu          # the reference moves the operands to the GPU when use_gpu is set; here ALWAYS
     if torch.cuda.is_available():   # (without CUDA the kernels below raise: there is no CPU fallback)
         dev = Q.device if Q.is_cuda else (D_padded.device if D_padded.is_cuda
                                           else torch.device("cuda", torch.cuda.current_device()))
         Q, D_padded, D_mask = Q.to(dev), D_padded.to(dev), D_mask.to(dev)
     if Q.size(0) == 1:
-        return all_pairs_maxsim(Q, D_padded, D_mask)[0]
-    return _aligned_maxsim(Q, D_padded, D_mask)
+        return _AllPairsMaxSim.apply(Q, D_padded, D_mask, flipr_maxlen)[0]
+    return _aligned_maxsim(Q, D_padded, D_mask, flipr_maxlen)
 
 
 class _GatherCat(torch.autograd.Function):

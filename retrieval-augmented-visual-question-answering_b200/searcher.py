@@ -181,6 +181,11 @@ class Searcher:
                                                  config, run_cfg)
         except Exception:          # foreign config type with a different constructor: keep what was given
             self.config = config
+        if getattr(self.config, "interaction", "colbert") != "colbert":
+            # the fused scan reduces with the plain sum of colbert_score_reduce (colbert.py:263); ranking a corpus
+            # by the 'flipr' partial top-k sums (:248-261, unused by FLMR) is only available through colbert_score
+            raise NotImplementedError("Searcher ranks with interaction='colbert'; got %r"
+                                      % (self.config.interaction,))
         if shard_across_ranks:
             import torch.distributed as dist
             from .maxsim import topk_merge

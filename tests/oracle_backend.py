@@ -107,10 +107,11 @@ def install(monkeypatch):
             for t in range(a.shape[1]):
                 p = b * stride + t
                 j = a[b, t]
-                if (j < 0).any() or g[b, t] == 0.0:
+                live = j >= 0                    # per token, like the kernels (fully masked document, or a token
+                if g[b, t] == 0.0 or not live.any():   # the 'flipr' reduction did not select)
                     continue
-                dQ[b] += g[b, t] * Dn[p, j]
-                np.add.at(dD[p], j, g[b, t] * Qn[b])
+                dQ[b][live] += g[b, t] * Dn[p, j[live]]
+                np.add.at(dD[p], j[live], g[b, t] * Qn[b][live])
         return (torch.from_numpy(dQ) if need_dq else None, torch.from_numpy(dD) if need_dd else None)
 
     def maxsim_argmax(Q, D, mask, return_rowmax=False):

@@ -358,3 +358,28 @@ def test_graphed_loss_step_replays_the_eager_step(argmax_path):
             assert torch.equal(Qa.grad, Qb.grad)
             # dD is scattered with fp32 atomics: equal up to the order of the additions
             np.testing.assert_allclose(Da.grad.cpu().numpy(), Db.grad.cpu().numpy(), rtol=1e-5, atol=1e-7)
+
+
+@pytest.mark.parametrize("nq", [96, 70])
+def test_flipr_interaction_matches_reference_golden(nq):
+    """``interaction == 'flipr'`` (colbert_score_reduce, colbert.py:248-261): scores and gradients of both caller
+    shapes against what the reference's own ColBERT.score + autograd produced (tests/golden/make_golden_flipr.py)."""
+    import os
+    import types
+    import ravqa_b200 as R
+    from helpers import GOLDEN_DIR, bf16_bits_to_f32
+    z = np.load(os.path.join(GOLDEN_DIR, "flipr.npz"))
+    k = "nq%d_" % nq
+    cfg = types.SimpleNamespace(interaction="flipr", query_maxlen=64)
+    r = int(z["docs_per_query"])
+    w = torch.from_numpy(z["weights"]).cuda()
+    mask = torch.from_numpy(z[k + "mask"]).cuda().unsqueeze(-1)
+    for shape in ("aligned", "one"):
+        Q = torch.from_numpy(bf16_bits_to_f32(z[k + "Q_bf16"])).cuda().requires_grad_(True)
+        D = torch.from_numpy(bf16_bits_to_f32(z[k + "D_bf16"])).cuda().requires_grad_(True)
+        Qin = Q.repeat_interleave(r, dim=0).contiguous() if shape == "aligned" else Q[:1]
+        s = R.colbert_score(Qin, D, mask, config=cfg)
+        (s * w).sum().backward()
+        np.testing.assert_allclose(s.detach().cpu().numpy(), z[k + shape], rtol=2e-5)
+        np.testing.assert_allclose(Q.grad.cpu().numpy(), z[k + shape + "_dQ"], rtol=1e-3, atol=1e-6)
+        np.testing.assert_allclose(D.grad.cpu().numpy(), z[k + shape + "_dD"], rtol=1e-3, atol=1e-6)

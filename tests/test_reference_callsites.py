@@ -363,3 +363,45 @@ def test_reference_colbert_methods_route_into_this_backend(ref, monkeypatch):
     for a, b in zip(after["train"], before["train"]):
         np.testing.assert_allclose(a.numpy(), b.numpy(), rtol=1e-4, atol=1e-5)
     assert ColBERT.compute_ib_loss_new is _Model.__dict__["compute_ib_loss_new"]   # restored
+
+
+@needs_reference
+@pytest.mark.parametrize("nq", [64, 70, 72, 96])
+def test_flipr_interaction_equals_reference(ref, monkeypatch, nq):
+    """``config.interaction == 'flipr'`` (colbert_score_reduce, colbert.py:248-261; unused by FLMR): this package's
+    ``colbert_score`` against the reference's own — one query vs all documents and aligned pairs, values and
+    gradients — with fewer than 8 (no second term), exactly 8 and more tokens beyond ``query_maxlen``."""
+    import oracle_backend
+    import ravqa_b200 as R
+    oracle_backend.install(monkeypatch)
+    from colbert.infra import ColBERTConfig as RC
+    from colbert.modeling.colbert import colbert_score as ref_score
+    cfg = RC(total_visible_gpus=0, interaction="flipr", query_maxlen=64)
+    g = torch.Generator().manual_seed(nq)
+    n, nd = 5, 30
+    Q0 = torch.nn.functional.normalize(torch.randn(n, nq, 128, generator=g), dim=-1).bfloat16().float()
+    D0 = torch.nn.functional.normalize(torch.randn(n, nd, 128, generator=g), dim=-1).bfloat16().float()
+    M0 = torch.rand(n, nd, 1, generator=g) > 0.3
+    M0[:, 0] = True
+    w = torch.linspace(0.5, 1.5, n)
+    for q_rows in (slice(0, 1), slice(0, n)):
+        out = []
+        for fn in (ref_score, R.colbert_score):
+            Q, D = Q0[q_rows].clone().requires_grad_(True), D0.clone().requires_grad_(True)
+            s = fn(Q, D, M0, config=cfg) if fn is R.colbert_score else fn(Q, D * M0, M0, config=cfg, use_gpu=False)
+            (s * w).sum().backward()
+            out.append((s.detach(), Q.grad.clone(), D.grad.clone()))
+        for a, b in zip(*out):
+            np.testing.assert_allclose(b.numpy(), a.numpy(), rtol=1e-5, atol=1e-6)
+    # and it is not the plain sum
+    assert not torch.allclose(R.colbert_score(Q0[:1], D0, M0, config=cfg), R.colbert_score(Q0[:1], D0, M0))
+    # packed form (colbert.py:289-311: 'flipr' always takes the padded reduction)
+    from colbert.modeling.colbert import colbert_score_packed as ref_packed
+    import ravqa_b200.integration as I
+    lens = torch.tensor([30, 7, 19, 1, 24])
+    packed = torch.cat([D0[i, :l] for i, l in enumerate(lens)])
+    want = ref_packed(Q0[:1], packed, lens, cfg)
+    got = I.colbert_score_packed(Q0[:1], packed, lens, cfg)
+    np.testing.assert_allclose(got.numpy(), want.numpy(), rtol=1e-5)
+    with pytest.raises(NotImplementedError):
+        R.Searcher(index=oracle_backend.OracleCorpus(packed, lens), config=cfg)
