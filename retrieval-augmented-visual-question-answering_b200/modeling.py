@@ -253,14 +253,25 @@ class _GatherCat(torch.autograd.Function):
         import torch.distributed as dist
         world = dist.get_world_size(group)
         ctx.group, ctx.rank, ctx.rows = group, dist.get_rank(group), x.size(0)
+        ctx.flat = x.is_cuda and dist.get_backend(group) == "nccl"
+        x = x.contiguous()
+        if ctx.flat:      # one collective straight into the concatenated tensor (no list of outputs, no cat)
+            out = x.new_empty((world * x.size(0),) + tuple(x.shape[1:]))
+            dist.all_gather_into_tensor(out, x, group=group)
+            return out
         outs = [torch.empty_like(x) for _ in range(world)]
-        dist.all_gather(outs, x.contiguous(), group=group)
+        dist.all_gather(outs, x, group=group)
         return torch.cat(outs, dim=0)
 
     @staticmethod
     def backward(ctx, g: torch.Tensor):
         import torch.distributed as dist
-        g = g.contiguous().clone()
+        g = g.contiguous()
+        if ctx.flat:      # every rank needs only the sum over ranks of ITS rows: reduce-scatter, half an all-reduce
+            out = g.new_empty((ctx.rows,) + tuple(g.shape[1:]))
+            dist.reduce_scatter_tensor(out, g, op=dist.ReduceOp.SUM, group=ctx.group)
+            return out, None
+        g = g.clone()
         dist.all_reduce(g, op=dist.ReduceOp.SUM, group=ctx.group)
         return g[ctx.rank * ctx.rows:(ctx.rank + 1) * ctx.rows], None
 
@@ -307,6 +318,10 @@ def in_batch_negatives_loss(Q: torch.Tensor, D_padded: torch.Tensor, D_mask: tor
             raise RuntimeError("cross_rank_negatives needs an initialised torch.distributed process group")
         first = dist.get_rank(group) * B * nway
         D_padded, D_mask = gather_documents(D_padded, D_mask, group)
+        if (all_pairs_fn is None and not return_scores and Q.is_cuda
+                and float(B) * D_padded.size(0) * Q.size(1) * 8 <= _FUSED_MAX_ARG_BYTES):
+            # same fused route as the single-rank batch, the positives shifted to this rank's columns
+            return _FusedIBLoss.apply(Q, D_padded, D_mask, int(nway), int(first))[0]
     scores = score_fn(Q, D_padded, D_mask)                                # [B, (world*)B*nway]
     labels = first + torch.arange(B, device=scores.device) * nway
     loss = torch.nn.functional.cross_entropy(scores, labels)

@@ -198,6 +198,14 @@ def _nccl_ib_worker(rank, world, port, ret):
           and torch.allclose(loss.detach(), losses[rank].detach(), rtol=1e-5, atol=1e-6)
           and torch.allclose(Q.grad, Qs[rank].grad, rtol=1e-3, atol=1e-6)
           and torch.allclose(D.grad, Ds[rank].grad, rtol=1e-3, atol=1e-6))
+    # the loss-only call takes the fused route (arg-max kernel + loss head with this rank's label offset,
+    # all-gather straight into the concatenated tensor, reduce-scatter of the document gradient)
+    Q2, D2 = Q.detach().clone().requires_grad_(True), D.detach().clone().requires_grad_(True)
+    loss2 = R.in_batch_negatives_loss(Q2, D2, m.unsqueeze(-1), nway, cross_rank_negatives=True)
+    loss2.backward()
+    ok = (ok and torch.allclose(loss2.detach(), losses[rank].detach(), rtol=1e-5, atol=1e-6)
+          and torch.allclose(Q2.grad, Qs[rank].grad, rtol=1e-3, atol=1e-6)
+          and torch.allclose(D2.grad, Ds[rank].grad, rtol=1e-3, atol=1e-6))
     ret[rank] = bool(ok)
     dist.barrier()
     dist.destroy_process_group()
