@@ -190,7 +190,7 @@ def multi_gpu():
         print("| C4 loss step on %d ranks (bsz %d = %d per rank, nway 2, Nq 832, Nd 512), max over ranks | ms |\n|---|---:|"
               % (world, B * world, B))
         print("| local in-batch negatives only (the reference's behaviour, colbert.py:69 commented out) | %.3f |" % out[False])
-        print("| cross-rank negatives: all-gather of D + [8, %d] matrix per rank + all-reduce of dD | %.3f |"
+        print("| cross-rank negatives: all-gather of D + [8, %d] matrix per rank + reduce-scatter of dD | %.3f |"
               % (B * nway * world, out[True]))
     dist.destroy_process_group()
 
