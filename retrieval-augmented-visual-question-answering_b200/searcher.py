@@ -6,7 +6,8 @@
         searcher = Searcher(index="temp_index.nbits=8", config=ColBERTConfig(total_visible_gpus=...))
     ._search_all_Q(queries, Q, k, filter_fn=None, progress=True, remove_zero_tensors=False) -> Ranking
     .dense_search(Q[1,Nq,d], k, filter_fn=None, remove_zero_tensors=False) -> (pids, ranks, scores)
-    .search(text, k) / .search_all(queries, k)        (need an ``encode_fn``: encoders stay PyTorch)
+    .search(text, k) / .search_all(queries, k)        (``encode_fn``, or the reference's ``Checkpoint`` built lazily
+                                                       from ``checkpoint``: encoders stay PyTorch)
     Ranking.todict() -> {qid: [(pid, rank, score), ...]}   (colbert/data/ranking.py:48)
 
 The index is addressed exactly as the reference does (``<Run().root>/<experiment>/indexes/<index>``,
@@ -152,6 +153,7 @@ class Searcher:
         self.query_batch = int(query_batch)
         self._sharded = None
         self._nccl = None
+        self._checkpoint_model = None
         self.index_config = None
         run_cfg = active_run_config(config)
         if isinstance(index, FlatCorpus):
@@ -212,19 +214,46 @@ class Searcher:
             self.config.configure(**kw)
         return self
 
+    def _text_encoder(self):
+        """The reference's own query encoder, built on first use as searcher.py:31-43 does at construction:
+        ``Checkpoint(checkpoint or index_config.checkpoint, colbert_config=self.config)`` from the reference's
+        ``colbert`` package (it stays PyTorch; nothing of it is reimplemented here)."""
+        if self._checkpoint_model is None:
+            name = self.checkpoint or getattr(self.index_config, "checkpoint", None)
+            if name is None:
+                raise RuntimeError("text search needs encode_fn=... or checkpoint=... (the query encoder stays in "
+                                   "PyTorch: FLMR.query / Checkpoint.queryFromText, out of scope here)")
+            try:
+                from colbert.modeling.checkpoint import Checkpoint
+            except ImportError as e:
+                raise RuntimeError("text search with checkpoint=%r needs the reference's colbert package on "
+                                   "sys.path (third_party/ColBERT), or pass encode_fn=..." % (name,)) from e
+            model = Checkpoint(name, colbert_config=self.config)
+            self._checkpoint_model = model.cuda() if torch.cuda.is_available() else model
+        return self._checkpoint_model
+
     def encode(self, text, full_length_search=False):
-        if self.encode_fn is None:
-            raise RuntimeError("text search needs encode_fn=...; the query encoder stays in PyTorch "
-                               "(FLMR.query / Checkpoint.queryFromText) and is out of scope here")
+        """searcher.py:52-59.  ``encode_fn`` (queries -> ``[n, Nq, d]``) when given, else the reference's
+        ``Checkpoint.queryFromText``; the embeddings stay on the GPU (the reference moves them to the CPU)."""
         queries = text if isinstance(text, list) else [text]
-        return self.encode_fn(queries)
+        if self.encode_fn is not None:
+            return self.encode_fn(queries)
+        model = self._text_encoder()
+        bsize = 128 if len(queries) > 128 else None
+        maxlen = getattr(self.config, "query_maxlen", None)
+        if maxlen is not None and hasattr(model, "query_tokenizer"):
+            model.query_tokenizer.query_maxlen = maxlen
+        return model.queryFromText(queries, bsize=bsize, to_cpu=False)
 
     def search(self, text: str, k: int = 10, filter_fn=None):
         return self.dense_search(self.encode(text), k, filter_fn=filter_fn)
 
     def search_all(self, queries, k: int = 10, filter_fn=None):
         texts = list(queries.values()) if hasattr(queries, "values") else list(queries)
-        return self._search_all_Q(queries, self.encode(texts), k, filter_fn=filter_fn)
+        Q = self.encode(texts)
+        if isinstance(Q, (list, tuple)):               # queryFromText with a batch size returns per-batch tensors
+            Q = torch.cat(list(Q))
+        return self._search_all_Q(queries, Q, k, filter_fn=filter_fn)
 
     @staticmethod
     def _drop_zero_rows(Q: torch.Tensor) -> torch.Tensor:

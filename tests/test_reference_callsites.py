@@ -405,3 +405,52 @@ def test_flipr_interaction_equals_reference(ref, monkeypatch, nq):
     np.testing.assert_allclose(got.numpy(), want.numpy(), rtol=1e-5)
     with pytest.raises(NotImplementedError):
         R.Searcher(index=oracle_backend.OracleCorpus(packed, lens), config=cfg)
+
+
+@needs_reference
+def test_text_search_goes_through_the_references_checkpoint(ref, golden, monkeypatch):
+    """``Searcher.search`` / ``search_all`` (searcher.py:52-71) with ``checkpoint=``: the query encoder is the
+    reference's own ``colbert.modeling.checkpoint.Checkpoint``, constructed lazily with (name, colbert_config=
+    searcher.config) and asked through ``queryFromText`` exactly as the reference's ``encode`` does — here a recording
+    stand-in with the same constructor and method (no BERT weights offline) that returns the golden query
+    embeddings, so the ranking is the exact one."""
+    import oracle_backend
+    import ravqa_b200 as R
+    import colbert.modeling.checkpoint as CK
+    from colbert.data import Queries
+    from colbert.infra import ColBERTConfig, Run, RunConfig
+    oracle_backend.install(monkeypatch)
+    monkeypatch.setattr(torch.cuda, "is_available", lambda: False)
+    seen = {}
+    Qg = torch.from_numpy(golden["queries"])
+    texts = ["question %d" % i for i in range(Qg.size(0))]
+
+    class FakeCheckpoint:
+        def __init__(self, name, colbert_config=None):
+            seen["ctor"] = (name, colbert_config)
+            self.query_tokenizer = type("T", (), {"query_maxlen": None})()
+
+        def queryFromText(self, queries, bsize=None, to_cpu=False, context=None):
+            seen.setdefault("calls", []).append((list(queries), bsize, to_cpu, self.query_tokenizer.query_maxlen))
+            return torch.stack([Qg[texts.index(q)] for q in queries])
+
+    monkeypatch.setattr(CK, "Checkpoint", FakeCheckpoint)
+    with Run().context(RunConfig(nranks=1, rank=0, root=CKPT_DIR, experiment="temp_index_0")):
+        searcher = R.Searcher(index="temp_index.nbits=8", checkpoint="some/checkpoint",
+                              config=ColBERTConfig(total_visible_gpus=0, query_maxlen=48))
+    assert "ctor" not in seen                                        # nothing is loaded until text arrives
+    k = int(golden["k"])
+    want = np.argsort(-golden["exact_scores_bf16"], axis=1, kind="stable")[:, :k]
+    pids, ranks, scores = searcher.search(texts[3], k=k)
+    assert seen["ctor"][0] == "some/checkpoint" and seen["ctor"][1] is searcher.config
+    assert seen["calls"][0] == ([texts[3]], None, False, 48)
+    assert pids == want[3].tolist() and ranks == list(range(1, k + 1))
+    ranking = searcher.search_all(Queries(data=dict(zip(["a%d" % i for i in range(len(texts))], texts))), k=k)
+    assert [[e[0] for e in v] for v in ranking.todict().values()] == want.tolist()
+    assert len(seen["calls"]) == 2 and seen["calls"][1][0] == texts
+    # no checkpoint and no encode_fn: a clear error instead of a silent CPU path
+    with Run().context(RunConfig(nranks=1, rank=0, root=CKPT_DIR, experiment="temp_index_0")):
+        bare = R.Searcher(index="temp_index.nbits=8", config=ColBERTConfig(total_visible_gpus=0))
+    bare.index_config.checkpoint = None
+    with pytest.raises(RuntimeError, match="encode_fn"):
+        bare.search("text", k=3)
