@@ -24,6 +24,7 @@ from typing import Callable, Optional, Sequence
 import torch
 
 from .index_io import chunk_exists, finalize_chunked_index, save_flat_chunk
+from .infra import resolve_index_path, run_context_open
 
 
 class Indexer:
@@ -32,7 +33,8 @@ class Indexer:
         self.checkpoint = checkpoint
         self.config = config
         self.encode_fn = encode_fn
-        self.index_root = index_root or (getattr(config, "index_root_", None) if config is not None else None)
+        self.index_root = index_root      # None: addressed through config + the Run() context, like the reference
+        self._checkpoint_model = None
         self.chunksize = int(chunksize)
         self.rank, self.nranks = int(rank), int(nranks)
         self.index_path = None
@@ -51,7 +53,42 @@ class Indexer:
         return deleted
 
     def _path(self, name: str) -> str:
-        return name if (os.path.isabs(name) or self.index_root is None) else os.path.join(self.index_root, name)
+        """colbert/indexer.py:66-68 (``config.index_path_`` after ``from_existing(checkpoint_config, config,
+        Run().config)``): ``<root>/<experiment>/indexes/<name>`` of the open Run context unless an explicit
+        ``index_root=`` (an extension) or an absolute name says otherwise."""
+        if os.path.isabs(name):
+            return name
+        if self.index_root is None and self.config is None and not run_context_open():
+            return name                                  # no config, no context: relative to the working directory
+        return resolve_index_path(name, self.config, self.index_root)
+
+    def _reference_encode_fn(self) -> Callable:
+        """Document encoder of the reference, built on first use: ``Checkpoint(checkpoint, colbert_config=config)``
+        and the batching of ``CollectionEncoder.encode_passages`` (collection_encoder.py:13-45) around its
+        ``docFromText(..., keep_dims='flatten')``.  It stays PyTorch; nothing of it is reimplemented here."""
+        if self._checkpoint_model is None:
+            if self.checkpoint is None:
+                raise RuntimeError("Indexer needs encode_fn=... or checkpoint=...: the document encoder (ColBERT.doc "
+                                   "/ Checkpoint.docFromText) stays in PyTorch and is out of scope here")
+            try:
+                from colbert.modeling.checkpoint import Checkpoint
+            except ImportError as e:
+                raise RuntimeError("Indexer(checkpoint=%r) needs the reference's colbert package on sys.path "
+                                   "(third_party/ColBERT), or pass encode_fn=..." % (self.checkpoint,)) from e
+            model = Checkpoint(self.checkpoint, colbert_config=self.config)
+            self._checkpoint_model = model.cuda() if torch.cuda.is_available() else model
+        model, bsize = self._checkpoint_model, int(getattr(self.config, "bsize", 32) or 32)
+
+        def encode(passages):
+            embs, doclens = [], []
+            with torch.inference_mode():
+                for b0 in range(0, len(passages), bsize * 50):
+                    e, d = model.docFromText(passages[b0:b0 + bsize * 50], bsize=bsize, keep_dims="flatten",
+                                             showprogress=False)
+                    embs.append(e)
+                    doclens.extend(d)
+            return torch.cat(embs), doclens
+        return encode
 
     def _barrier(self) -> None:
         """All ranks of a multi-rank build meet here.  The reference erases and plans in the parent process before
@@ -63,11 +100,26 @@ class Indexer:
                                    "erases / finalizes, the others must wait for it" % self.nranks)
             torch.distributed.barrier()
 
+    @staticmethod
+    def _cast_collection(collection) -> Sequence:
+        """colbert.data.Collection.cast (collection.py:86-96): a list of passages, an object with ``data``, or the
+        path of a ``pid \\t passage [\\t title]`` TSV (evaluation/loaders.py:155-176: title is prepended with ' | ')."""
+        if isinstance(collection, str):
+            out = []
+            with open(collection) as f:
+                for line_idx, line in enumerate(f):
+                    pid, passage, *rest = line.strip("\n\r ").split("\t")
+                    assert pid == "id" or int(pid) == line_idx, (pid, line_idx)
+                    out.append(rest[0] + " | " + passage if rest else passage)
+            return out
+        data = getattr(collection, "data", None)
+        return collection if data is None else data
+
     def index(self, name: str, collection: Sequence, overwrite=False) -> str:
         assert overwrite in [True, False, "reuse", "resume"]
+        collection = self._cast_collection(collection)
         if self.encode_fn is None:
-            raise RuntimeError("Indexer needs encode_fn=...: the document encoder (ColBERT.doc / "
-                               "Checkpoint.docFromText) stays in PyTorch and is out of scope here")
+            self.encode_fn = self._reference_encode_fn()
         self.index_path = self._path(name)
         # rank 0 decides about the directory (exists? erase?) BEFORE any rank writes a chunk into it; the others
         # wait at the barrier, so a fast rank can neither have its chunks erased nor trip the exists-check

@@ -248,6 +248,14 @@ def active_run_config(config=None):
     return ref if (ref_open and len(Run().stack) == 1) else ours
 
 
+def run_context_open() -> bool:
+    """Is a ``Run().context(...)`` open — this package's or the reference's (when its package is loaded)?"""
+    if len(Run().stack) > 1:
+        return True
+    mod = sys.modules.get("colbert.infra.run")
+    return mod is not None and len(mod.Run().stack) > 1
+
+
 def _overlay(sources: Iterable, keys=("index_root", "root", "experiment")) -> Dict[str, object]:
     """Assigned fields of ``sources`` overlaid in order (later wins) — ``from_existing`` restricted to the
     fields that address an index."""

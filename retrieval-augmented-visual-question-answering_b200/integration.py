@@ -18,8 +18,11 @@ What is replaced (reference -> here):
     ColBERT.compute_ib_loss_new                                          -> integration.compute_ib_loss_new
         (colbert.py:82-113: materialises [B, B*nway, Nd, Nq]; here one fused all-pairs launch)
 
+    colbert.Indexer (opt-in: ``patch_colbert(indexer=True)``)            -> ravqa_b200.Indexer
+        (indexer.py:16-84, caller FLMR_executor.py:601-617: flat bf16 store instead of the PLAID build)
+
 Nothing of the reference is modified on disk; ``unpatch_colbert()`` restores the originals.  Encoders, data
-pipeline, executors and the PLAID index *build* stay the reference's own.
+pipeline, executors and (unless opted out of as above) the PLAID index *build* stay the reference's own.
 """
 from __future__ import annotations
 
@@ -96,14 +99,25 @@ def _rebind_everywhere(old, new) -> int:
     return n
 
 
-def patch_colbert(searcher: bool = True, scoring: bool = True, ib_loss: bool = True) -> Dict[str, int]:
+def patch_colbert(searcher: bool = True, scoring: bool = True, ib_loss: bool = True, indexer: bool = False
+                  ) -> Dict[str, int]:
     """Install the replacements listed in the module docstring into the loaded ``colbert`` package (imports it
     if needed: ``third_party/ColBERT`` must be on ``sys.path`` as the reference arranges).  Returns how many
-    module globals were rebound per replaced object."""
+    module globals were rebound per replaced object.
+
+    ``indexer=True`` (opt-in) also replaces ``colbert.Indexer`` (indexer.py:16, called at FLMR_executor.py:601-617)
+    by ``ravqa_b200.Indexer``: same constructor and ``index(name, collection, overwrite)``, the reference's own
+    ``Checkpoint`` as document encoder, but the embeddings are stored flat in bf16 — no k-means, residual codec or
+    IVF — where the reference would put its PLAID directory; ``Searcher`` opens either kind."""
     import colbert                                      # noqa: F401  (the reference's vendored package)
     import colbert.modeling.colbert as M
     import colbert.searcher as S
     done: Dict[str, int] = {}
+    if indexer:
+        import colbert.indexer as IX
+        from .indexer import Indexer
+        if IX.Indexer is not Indexer:
+            done["Indexer"] = _rebind_everywhere(IX.Indexer, Indexer)
     if searcher and S.Searcher is not Searcher:
         done["Searcher"] = _rebind_everywhere(S.Searcher, Searcher)
     if scoring:

@@ -454,3 +454,76 @@ def test_text_search_goes_through_the_references_checkpoint(ref, golden, monkeyp
     bare.index_config.checkpoint = None
     with pytest.raises(RuntimeError, match="encode_fn"):
         bare.search("text", k=3)
+
+
+@needs_reference
+def test_indexer_with_the_references_checkpoint_and_run_context(ref, monkeypatch, tmp_path):
+    """``Indexer(checkpoint=..., config=...).index(name=..., collection=..., overwrite=True)`` as
+    FLMR_executor.py:601-617 calls it, inside the reference's ``Run().context``: the document encoder is the
+    reference's ``Checkpoint`` (a recording stand-in here: no BERT weights offline) driven with the batching of
+    ``CollectionEncoder.encode_passages``; the flat index lands where ``config.index_path_`` points
+    (``<root>/<experiment>/indexes/<name>``), and ``Searcher(index=name)`` in the same context opens and ranks it."""
+    import zlib
+    import oracle_backend
+    import ravqa_b200 as R
+    import colbert.modeling.checkpoint as CK
+    from colbert.infra import ColBERTConfig, Run, RunConfig
+    oracle_backend.install(monkeypatch)
+    monkeypatch.setattr(torch.cuda, "is_available", lambda: False)
+    seen = {"batches": []}
+
+    def embed(text):
+        g = torch.Generator().manual_seed(zlib.crc32(text.encode()))
+        n = 3 + zlib.crc32(text.encode()) % 6
+        return torch.nn.functional.normalize(torch.randn(n, 128, generator=g), dim=-1)
+
+    class FakeCheckpoint:
+        def __init__(self, name, colbert_config=None):
+            seen["ctor"] = (name, colbert_config)
+
+        def docFromText(self, docs, bsize=None, keep_dims=True, to_cpu=False, showprogress=False, return_tokens=False):
+            assert keep_dims == "flatten" and torch.is_inference_mode_enabled()
+            seen["batches"].append((len(docs), bsize))
+            embs = [embed(d) for d in docs]
+            return torch.cat(embs), [e.size(0) for e in embs]
+
+    monkeypatch.setattr(CK, "Checkpoint", FakeCheckpoint)
+    collection = ["passage number %d" % i for i in range(230)]
+    with Run().context(RunConfig(nranks=1, rank=0, root=str(tmp_path), experiment="temp_index_0")):
+        config = ColBERTConfig(nbits=8, doc_maxlen=512, total_visible_gpus=0, bsize=2)
+        indexer = R.Indexer(checkpoint="a/checkpoint", config=config)
+        path = indexer.index(name="temp_index.nbits=8", collection=collection, overwrite=True)
+        assert path == os.path.join(str(tmp_path), "temp_index_0", "indexes", "temp_index.nbits=8")
+        assert path == ColBERTConfig.from_existing(config, Run().config).index_root_ + "temp_index.nbits=8" \
+            or os.path.normpath(path) == os.path.normpath(os.path.join(
+                ColBERTConfig.from_existing(config, Run().config).index_root_, "temp_index.nbits=8"))
+        assert seen["ctor"] == ("a/checkpoint", config)
+        assert seen["batches"] == [(100, 2), (100, 2), (30, 2)]           # bsize * 50 passages per docFromText call
+        searcher = R.Searcher(index="temp_index.nbits=8", config=ColBERTConfig(total_visible_gpus=0))
+    assert searcher.index_kind == "flat" and searcher.corpus.n_passages == len(collection)
+    Q = torch.stack([torch.nn.functional.pad(embed(collection[i]), (0, 0, 0, 8 - embed(collection[i]).size(0)))
+                     for i in (7, 100, 229)])
+    ranking = searcher._search_all_Q(None, Q, k=3).todict()
+    assert [v[0][0] for v in ranking.values()] == [7, 100, 229]          # each passage's own tokens find it first
+    # opt-in: `from colbert import Indexer` itself becomes the flat-store Indexer; a TSV path is a collection too
+    import ravqa_b200.integration as flmr_b200
+    import colbert.indexer
+    original = colbert.indexer.Indexer
+    tsv = tmp_path / "collection.tsv"
+    tsv.write_text("".join("%d\t%s\ttitle %d\n" % (i, t, i) for i, t in enumerate(collection[:20])))
+    try:
+        assert flmr_b200.patch_colbert(searcher=False, scoring=False, ib_loss=False, indexer=True)["Indexer"] >= 2
+        from colbert import Indexer
+        assert Indexer is R.Indexer
+        with Run().context(RunConfig(nranks=1, root=str(tmp_path), experiment="temp_index_1")):
+            indexer = Indexer(checkpoint="a/checkpoint", config=ColBERTConfig(nbits=2, bsize=4))
+            indexer.index(name="temp_index.nbits=2", collection=str(tsv), overwrite=True)
+            index_path = indexer.get_index()
+        assert index_path == os.path.join(str(tmp_path), "temp_index_1", "indexes", "temp_index.nbits=2")
+        from ravqa_b200.index_io import load_flat_index
+        tokens, doclens, meta = load_flat_index(index_path)
+        want = [embed("title %d | %s" % (i, t)).size(0) for i, t in enumerate(collection[:20])]
+        assert doclens.tolist() == want and tokens.size(0) == sum(want)
+    finally:
+        flmr_b200.unpatch_colbert()
+    assert colbert.indexer.Indexer is original
